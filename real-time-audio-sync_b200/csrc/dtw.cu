@@ -1,0 +1,452 @@
+// K2/K3 — full DTW for a batch of independent pairs on sm_100a.
+//
+// Replaces dtw.DTW (reference dtw.py:5-53).  The N x M cost and accumulated-cost
+// matrices are never written to HBM: the cosine cost 1 - a_i.b_j (K = 12) is
+// computed inline inside a skewed warp wavefront, and only a 2-bit direction code
+// per cell is stored (0 = left (i,j-1), 1 = up (i-1,j), 2 = diag; dtw.py:30,38-40).
+//
+// Work decomposition
+//   band   = 128 consecutive rows (i) of one pair, swept over all N columns by ONE warp;
+//   lane l = rows band*128 + 4l .. +3, its 4 x 12 a-features live in registers;
+//   step s : lane l processes column j = s - l  (anti-diagonal skew inside the warp);
+//            the value under the lane's last row travels to lane l+1 by warp shuffle
+//            (the `up`/`diag` inputs of the next lane's first row);
+//   band b needs the last row of band b-1: it is streamed through an L2-resident
+//   ring of two rows per pair in chunks of 32 columns, guarded by a release/acquire
+//   progress counter per band.  Bands are claimed from one global atomic ticket in
+//   an order where every dependency has a smaller ticket (band-major, pairs
+//   interleaved), so a waiting warp always waits on a warp that is already running.
+//
+// Direction map layout (per pair): 16-byte units; unit (cbp, g) covers row group
+// g = i >> 2 (4 rows) and 16 consecutive SKEWED columns  jj = j + (g & 31),
+// cbp = jj >> 4.  Inside a unit: byte (jj & 15), bits 2*(i & 3).  The skew makes
+// all 32 lanes of a warp finish a unit on the same step, so a warp stores
+// 32 x 16 B = 512 contiguous bytes every 16 steps (unit index = cbp * gpad + g).
+#include <math_constants.h>
+
+#include <vector>
+
+#include "afs_common.cuh"
+
+namespace {
+
+constexpr int kF = 12;           // chroma features (F = 12 everywhere)
+constexpr int kRows = 4;         // rows per lane
+constexpr int kBandRows = 32 * kRows;
+constexpr int kWarpsPerBlock = 4;
+
+struct DtwPair {
+    int64_t a_off, b_off;   // element offsets of (12,M) / (12,N)
+    int64_t dir_off;        // uint4 units into the direction area
+    int64_t brow_off;       // elements into the hand-off area (2 rows of nsteps)
+    int64_t path_off;       // pairs into the path area
+    int32_t M, N;
+    int32_t nbands, gpad;   // gpad = nbands * 32 row groups
+    int32_t nsteps;         // roundup32(N + 31)
+    int32_t prog_off;       // first progress counter of this pair
+    int32_t path_cap;       // M + N
+    int32_t pad_;
+};
+
+struct DtwItem { int32_t pair, band; };
+
+template <typename T> struct Arith;
+template <> struct Arith<double> {
+    static __device__ __forceinline__ double inf() { return CUDART_INF; }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+};
+template <> struct Arith<float> {
+    static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+};
+
+template <typename T>
+struct DtwArgs {
+    const T *a, *b;
+    const DtwPair *pairs;
+    const DtwItem *items;
+    int n_items;
+    uint4 *dir;
+    T *brow;
+    int *prog;
+    int *ticket;
+    double *acc_end;
+    T *dense_cost, *dense_acc;
+};
+
+// Per-lane wavefront state.
+template <typename T>
+struct Lane {
+    T ar[kRows][kF];
+    T left[kRows];
+    T up_prev;
+    T bottom;
+};
+
+template <typename T, bool DENSE, int U>
+__device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane, const int band, const DtwPair &pm,
+                                         const T *__restrict__ bp, const T *ubuf, T *obuf, const bool feeds_next,
+                                         uint32_t &dw, const DtwArgs<T> &args, const int pair)
+{
+    using A = Arith<T>;
+    const unsigned full = 0xffffffffu;
+    const int N = pm.N;
+    const int j = s - lane;
+    // inputs for the lane's first row: value under the previous lane's last row, one step ago
+    T upn = __shfl_up_sync(full, L.bottom, 1);
+    T ub = ubuf[s & 31];
+    T up = (lane == 0) ? ub : upn;
+    if ((unsigned)j < (unsigned)N) {
+        T c[kRows];
+        {
+            T bk = __ldg(bp + j);
+#pragma unroll
+            for (int r = 0; r < kRows; r++) c[r] = A::mul(L.ar[r][0], bk);
+#pragma unroll
+            for (int k = 1; k < kF; k++) {
+                bk = __ldg(bp + (int64_t)k * N + j);
+#pragma unroll
+                for (int r = 0; r < kRows; r++) c[r] = A::fma(L.ar[r][k], bk, c[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < kRows; r++) c[r] = A::sub((T)1, c[r]);    // dtw.py:11
+        }
+        const bool origin = (band == 0) && (s == 0) && (lane == 0);      // dtw.py:20-21
+        T diag = L.up_prev;
+        T upv = up;
+        uint32_t nib = 0;
+#pragma unroll
+        for (int r = 0; r < kRows; r++) {
+            T x = A::add(L.left[r], c[r]);                  // (i, j-1)   dtw.py:35
+            T y = A::add(upv, c[r]);                        // (i-1, j)   dtw.py:36
+            T z = A::fma((T)2, c[r], diag);                 // (i-1, j-1) dtw.py:37 (2c exact)
+            if (r == 0 && origin) z = c[r];
+            const bool yx = y < x;                          // np.argmin: first minimum wins
+            T m = yx ? y : x;
+            const bool zm = z < m;
+            T v = zm ? z : m;
+            uint32_t code = zm ? 2u : (yx ? 1u : 0u);
+            nib |= code << (2 * r);
+            diag = L.left[r];
+            L.left[r] = v;
+            upv = v;
+            if (DENSE) {
+                const int64_t i = (int64_t)band * kBandRows + lane * kRows + r;
+                if (i < pm.M) {
+                    args.dense_cost[i * N + j] = c[r];
+                    args.dense_acc[i * N + j] = v;
+                }
+            }
+        }
+        L.up_prev = up;
+        L.bottom = L.left[kRows - 1];
+        dw |= nib << (8 * U);
+        if (feeds_next && lane == 31) obuf[s & 31] = L.bottom;
+        if (j == N - 1) {
+            const int rl = pm.M - 1 - (band * kBandRows + lane * kRows);   // row of (M-1) inside this lane
+            if (rl >= 0 && rl < kRows) {
+                T e = L.left[0];
+#pragma unroll
+                for (int r = 1; r < kRows; r++) if (rl == r) e = L.left[r];
+                args.acc_end[pair] = (double)e;
+            }
+        }
+    }
+}
+
+template <typename T, bool DENSE>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(const DtwArgs<T> args)
+{
+    using A = Arith<T>;
+    __shared__ T s_ubuf[kWarpsPerBlock][32];
+    __shared__ T s_obuf[kWarpsPerBlock][32];
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    T *ubuf = s_ubuf[w];
+    T *obuf = s_obuf[w];
+    const unsigned full = 0xffffffffu;
+
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(args.ticket, 1);
+        q = __shfl_sync(full, q, 0);
+        if (q >= args.n_items) break;
+        const DtwItem it = args.items[q];
+        const DtwPair pm = args.pairs[it.pair];
+        const int band = it.band;
+        const int N = pm.N;
+        const bool feeds_next = band + 1 < pm.nbands;
+        const T *ap = args.a + pm.a_off;
+        const T *bp = args.b + pm.b_off;
+        T *brow_cur = args.brow + pm.brow_off + (int64_t)(band & 1) * pm.nsteps;
+        const T *brow_prev = args.brow + pm.brow_off + (int64_t)((band + 1) & 1) * pm.nsteps;
+        int *prog_cur = args.prog + pm.prog_off + band;
+        const int *prog_prev = prog_cur - 1;
+        uint4 *dirp = args.dir + pm.dir_off + (int64_t)band * 32 + lane;
+
+        Lane<T> L;
+        {
+            const int r0 = band * kBandRows + lane * kRows;
+#pragma unroll
+            for (int k = 0; k < kF; k++)
+#pragma unroll
+                for (int r = 0; r < kRows; r++)
+                    L.ar[r][k] = (r0 + r < pm.M) ? __ldg(ap + (int64_t)k * pm.M + r0 + r) : (T)0;
+#pragma unroll
+            for (int r = 0; r < kRows; r++) L.left[r] = A::inf();
+            L.up_prev = A::inf();
+            L.bottom = A::inf();
+        }
+        __syncwarp();
+        ubuf[lane] = A::inf();          // band 0: nothing above the first row
+        __syncwarp();
+
+        uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+        for (int s0 = 0; s0 < pm.nsteps; s0 += 32) {
+            if (band > 0 && s0 < N) {
+                // wait until the band above has published columns [s0, s0+32)
+                const int need = min(s0 + 32, N);
+                while (afs::ld_acquire(prog_prev) < need) __nanosleep(40);
+                const int col = s0 + lane;
+                T v = (col < N) ? __ldcg(brow_prev + col) : A::inf();
+                __syncwarp();
+                ubuf[lane] = v;
+                __syncwarp();
+            }
+#pragma unroll 1
+            for (int g4 = 0; g4 < 8; g4++) {
+                const int s = s0 + g4 * 4;
+                uint32_t dw = 0;
+                dtw_step<T, DENSE, 0>(L, s + 0, lane, band, pm, bp, ubuf, obuf, feeds_next, dw, args, it.pair);
+                dtw_step<T, DENSE, 1>(L, s + 1, lane, band, pm, bp, ubuf, obuf, feeds_next, dw, args, it.pair);
+                dtw_step<T, DENSE, 2>(L, s + 2, lane, band, pm, bp, ubuf, obuf, feeds_next, dw, args, it.pair);
+                dtw_step<T, DENSE, 3>(L, s + 3, lane, band, pm, bp, ubuf, obuf, feeds_next, dw, args, it.pair);
+                d0 = d1; d1 = d2; d2 = d3; d3 = dw;
+                if ((g4 & 3) == 3) {
+                    const int cbp = s >> 4;
+                    __stcs(dirp + (int64_t)cbp * pm.gpad, make_uint4(d0, d1, d2, d3));
+                }
+            }
+            if (feeds_next) {
+                // slots 0..31 hold lane 31's columns s0-31 .. s0
+                __syncwarp();
+                const int col = s0 - 31 + lane;
+                if (col >= 0 && col < N) __stcg(brow_cur + col, obuf[lane]);
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) afs::st_release(prog_cur, min(s0 + 1, N));
+            }
+        }
+    }
+}
+
+// K3: backtrack over the direction map (dtw.py:43-52).  One warp per pair; lane 0
+// walks, writing the path back-to-front so that no reversal pass is needed.
+__global__ void dtw_backtrack_kernel(const DtwPair *pairs, int n_pairs, const uint4 *dir, int32_t *path,
+                                     int32_t *path_start, int32_t *path_len)
+{
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= n_pairs || (threadIdx.x & 31) != 0) return;
+    const DtwPair pm = pairs[p];
+    const uint8_t *dbytes = reinterpret_cast<const uint8_t *>(dir + pm.dir_off);
+    int2 *out = reinterpret_cast<int2 *>(path) + pm.path_off;
+    int i = pm.M - 1, j = pm.N - 1;
+    int pos = pm.path_cap - 1;
+    out[pos] = make_int2(i, j);
+    while (i > 0 || j > 0) {
+        const int g = i >> 2;
+        const int jj = j + (g & 31);
+        const int64_t unit = (int64_t)(jj >> 4) * pm.gpad + g;
+        const uint32_t byte = dbytes[unit * 16 + (jj & 15)];
+        const uint32_t code = (byte >> (2 * (i & 3))) & 3u;
+        if (code == 0) j -= 1;
+        else if (code == 1) i -= 1;
+        else { i -= 1; j -= 1; }
+        pos -= 1;
+        out[pos] = make_int2(i, j);
+    }
+    path_start[p] = pos;
+    path_len[p] = pm.path_cap - pos;
+}
+
+}  // namespace
+
+struct afs_dtw_plan {
+    int n_pairs = 0;
+    int dtype = AFS_F64;
+    std::vector<DtwPair> pairs;
+    std::vector<DtwItem> items;
+    DtwPair *d_pairs = nullptr;
+    DtwItem *d_items = nullptr;
+    size_t dir_bytes = 0, brow_bytes = 0, prog_bytes = 0;
+    int64_t total_path = 0;
+    int total_bands = 0;
+};
+
+extern "C" {
+
+int afs_dtw_plan_create(afs_dtw_plan **out, int n_pairs, const int64_t *h_len_a, const int64_t *h_len_b,
+                        const int64_t *h_off_a, const int64_t *h_off_b, int n_features, int dtype)
+{
+    if (!out || n_pairs <= 0 || !h_len_a || !h_len_b || !h_off_a || !h_off_b)
+        return afs::fail(AFS_ERR_INVALID, "afs_dtw_plan_create: null argument or n_pairs <= 0");
+    if (n_features != kF) return afs::fail(AFS_ERR_UNSUPPORTED, "afs_dtw: n_features must be 12 (got %d)", n_features);
+    if (dtype != AFS_F64 && dtype != AFS_F32) return afs::fail(AFS_ERR_INVALID, "afs_dtw: bad dtype %d", dtype);
+    afs_dtw_plan *pl = new afs_dtw_plan();
+    pl->n_pairs = n_pairs;
+    pl->dtype = dtype;
+    pl->pairs.resize(n_pairs);
+    int64_t dir_units = 0, brow_elems = 0, path_pairs = 0;
+    int prog = 0, max_bands = 0;
+    for (int p = 0; p < n_pairs; p++) {
+        const int64_t M = h_len_a[p], N = h_len_b[p];
+        if (M <= 0 || N <= 0 || M > (1 << 30) || N > (1 << 30)) {
+            delete pl;
+            return afs::fail(AFS_ERR_INVALID, "afs_dtw: pair %d has invalid lengths %lld x %lld", p, (long long)M, (long long)N);
+        }
+        DtwPair &q = pl->pairs[p];
+        q.a_off = h_off_a[p];
+        q.b_off = h_off_b[p];
+        q.M = (int32_t)M;
+        q.N = (int32_t)N;
+        q.nbands = (int32_t)((M + kBandRows - 1) / kBandRows);
+        q.gpad = q.nbands * 32;
+        q.nsteps = (int32_t)((N + 31 + 31) / 32 * 32);
+        q.dir_off = dir_units;
+        q.brow_off = brow_elems;
+        q.path_off = path_pairs;
+        q.prog_off = prog;
+        q.path_cap = (int32_t)(M + N);
+        q.pad_ = 0;
+        dir_units += (int64_t)(q.nsteps / 16) * q.gpad;
+        brow_elems += 2 * (int64_t)q.nsteps;
+        path_pairs += q.path_cap;
+        prog += q.nbands;
+        if (q.nbands > max_bands) max_bands = q.nbands;
+    }
+    // ticket order: band-major, pairs interleaved -> every dependency has a smaller ticket
+    for (int b = 0; b < max_bands; b++)
+        for (int p = 0; p < n_pairs; p++)
+            if (b < pl->pairs[p].nbands) pl->items.push_back(DtwItem{p, b});
+    pl->total_bands = prog;
+    pl->total_path = path_pairs;
+    pl->dir_bytes = afs::align_up((size_t)dir_units * 16, 256);
+    pl->brow_bytes = afs::align_up((size_t)brow_elems * (dtype == AFS_F64 ? 8 : 4), 256);
+    pl->prog_bytes = afs::align_up((size_t)(prog + 1) * sizeof(int), 256);
+    cudaError_t e = cudaMalloc(&pl->d_pairs, sizeof(DtwPair) * n_pairs);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_items, sizeof(DtwItem) * pl->items.size());
+    if (e == cudaSuccess) e = cudaMemcpy(pl->d_pairs, pl->pairs.data(), sizeof(DtwPair) * n_pairs, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->d_items, pl->items.data(), sizeof(DtwItem) * pl->items.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(pl->d_pairs);
+        cudaFree(pl->d_items);
+        delete pl;
+        return afs::fail(AFS_ERR_CUDA, "afs_dtw_plan_create: %s", cudaGetErrorString(e));
+    }
+    *out = pl;
+    return AFS_OK;
+}
+
+int afs_dtw_plan_destroy(afs_dtw_plan *pl)
+{
+    if (!pl) return AFS_OK;
+    cudaFree(pl->d_pairs);
+    cudaFree(pl->d_items);
+    delete pl;
+    return AFS_OK;
+}
+
+int afs_dtw_plan_workspace_bytes(const afs_dtw_plan *pl, size_t *bytes)
+{
+    if (!pl || !bytes) return afs::fail(AFS_ERR_INVALID, "afs_dtw_plan_workspace_bytes: null argument");
+    *bytes = pl->dir_bytes + pl->brow_bytes + pl->prog_bytes;
+    return AFS_OK;
+}
+
+int afs_dtw_plan_path_layout(const afs_dtw_plan *pl, int pair, int64_t *offset, int64_t *capacity)
+{
+    if (!pl || pair < -1 || pair >= pl->n_pairs) return afs::fail(AFS_ERR_INVALID, "afs_dtw_plan_path_layout: bad pair");
+    if (pair == -1) {   // total size of the path area
+        if (offset) *offset = 0;
+        if (capacity) *capacity = pl->total_path;
+        return AFS_OK;
+    }
+    if (offset) *offset = pl->pairs[pair].path_off;
+    if (capacity) *capacity = pl->pairs[pair].path_cap;
+    return AFS_OK;
+}
+
+}  // extern "C"
+
+template <typename T>
+static int launch_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b, void *ws, double *d_acc_end,
+                             void *dense_cost, void *dense_acc, cudaStream_t st)
+{
+    char *base = static_cast<char *>(ws);
+    DtwArgs<T> args;
+    args.a = static_cast<const T *>(d_a);
+    args.b = static_cast<const T *>(d_b);
+    args.pairs = pl->d_pairs;
+    args.items = pl->d_items;
+    args.n_items = (int)pl->items.size();
+    args.dir = reinterpret_cast<uint4 *>(base);
+    args.brow = reinterpret_cast<T *>(base + pl->dir_bytes);
+    args.prog = reinterpret_cast<int *>(base + pl->dir_bytes + pl->brow_bytes);
+    args.ticket = args.prog + pl->total_bands;
+    args.acc_end = d_acc_end;
+    args.dense_cost = static_cast<T *>(dense_cost);
+    args.dense_acc = static_cast<T *>(dense_acc);
+    AFS_CUDA(cudaMemsetAsync(args.prog, 0, pl->prog_bytes, st));
+    const bool dense = dense_cost != nullptr;
+    auto kern = dense ? dtw_wavefront_kernel<T, true> : dtw_wavefront_kernel<T, false>;
+    int occ = 0;
+    AFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerBlock * 32, 0));
+    if (occ < 1) return afs::fail(AFS_ERR_CUDA, "dtw kernel does not fit on an SM");
+    int blocks = afs::sm_count() * occ;
+    const int need = (args.n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks > need) blocks = need;
+    kern<<<blocks, kWarpsPerBlock * 32, 0, st>>>(args);
+    afs::count_launch();
+    AFS_CUDA(cudaGetLastError());
+    return AFS_OK;
+}
+
+extern "C" {
+
+int afs_dtw_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b, void *d_workspace, double *d_acc_end,
+                       void *d_dense_cost, void *d_dense_acc, void *stream)
+{
+    if (!pl || !d_a || !d_b || !d_workspace || !d_acc_end)
+        return afs::fail(AFS_ERR_INVALID, "afs_dtw_accumulate: null argument");
+    if ((d_dense_cost == nullptr) != (d_dense_acc == nullptr))
+        return afs::fail(AFS_ERR_INVALID, "afs_dtw_accumulate: dense cost and acc must be given together");
+    if (d_dense_cost && pl->n_pairs != 1)
+        return afs::fail(AFS_ERR_UNSUPPORTED, "afs_dtw_accumulate: dense outputs need a single-pair plan");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pl->dtype == AFS_F64)
+        return launch_accumulate<double>(pl, d_a, d_b, d_workspace, d_acc_end, d_dense_cost, d_dense_acc, st);
+    return launch_accumulate<float>(pl, d_a, d_b, d_workspace, d_acc_end, d_dense_cost, d_dense_acc, st);
+}
+
+int afs_dtw_backtrack(afs_dtw_plan *pl, const void *d_workspace, int32_t *d_path, int32_t *d_path_start,
+                      int32_t *d_path_len, void *stream)
+{
+    if (!pl || !d_workspace || !d_path || !d_path_start || !d_path_len)
+        return afs::fail(AFS_ERR_INVALID, "afs_dtw_backtrack: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int wpb = 2;
+    const int blocks = (pl->n_pairs + wpb - 1) / wpb;
+    dtw_backtrack_kernel<<<blocks, wpb * 32, 0, st>>>(pl->d_pairs, pl->n_pairs, static_cast<const uint4 *>(d_workspace),
+                                                      d_path, d_path_start, d_path_len);
+    afs::count_launch();
+    AFS_CUDA(cudaGetLastError());
+    return AFS_OK;
+}
+
+}  // extern "C"
