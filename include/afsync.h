@@ -99,11 +99,19 @@ int afs_otw_state_bytes(const afs_otw *h, size_t *bytes);
 /* bind + initialise the state block (must be called once before stepping; calling
  * it again resets every stream to the freshly constructed object) */
 int afs_otw_reset(afs_otw *h, void *d_state, void *stream);
+/* Put freshly reset streams into the state the reference's set_live() drivers
+ * (otw_eran.py:91-142, livenote_v2.py:108-155) have after their first loop-top
+ * best-point call: path = [(0,0)], run_count = 1.  Then afs_otw_step over the whole
+ * live sequence reproduces set_live's path. */
+int afs_otw_seed_set_live(afs_otw *h, void *stream);
+/* slots per (frame, stream) in d_points: max_run + 2 (an insert appends at most
+ * max_run + 1 points: the run-count limit bounds consecutive column steps) */
+int afs_otw_points_per_step(const afs_otw *h);
 /* Advance every stream by `n_frames` live frames.  d_frames is (n_frames, n_streams, 12)
  * double.  d_active (may be NULL) is n_streams bytes: 0 = skip this stream.
  * Per (frame, stream): d_status = AFS_STEP_*; d_npoints = points appended by that
- * insert (0..4); d_points (.., 4, 2) int32 = the appended (live, ref) pairs.
- * Any of the three outputs may be NULL. */
+ * insert; d_points (.., PTS, 2) int32 = the appended (live, ref) pairs, PTS =
+ * afs_otw_points_per_step().  Any of the three outputs may be NULL. */
 int afs_otw_step(afs_otw *h, const double *d_frames, int n_frames, const uint8_t *d_active,
                  int32_t *d_status, int32_t *d_npoints, int32_t *d_points, void *stream);
 /* Device-resident full paths: per stream, capacity and offset (in pairs) inside the

@@ -41,6 +41,8 @@ _SIGNATURES = {
     "afs_otw_destroy": (C.c_int, [_vp]),
     "afs_otw_state_bytes": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),
     "afs_otw_reset": (C.c_int, [_vp, _vp, _vp]),
+    "afs_otw_points_per_step": (C.c_int, [_vp]),
+    "afs_otw_seed_set_live": (C.c_int, [_vp, _vp]),
     "afs_otw_step": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "afs_otw_path_layout": (C.c_int, [_vp, C.c_int, _i64p, _i64p]),
     "afs_otw_path_ptr": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),

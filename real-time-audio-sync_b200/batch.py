@@ -1,0 +1,143 @@
+"""Batched front-ends: many independent streams / pairs / tracks per launch.
+
+``OtwBatch`` advances n independent OnlineTimeWarping / LiveNoteV2 / LiveNote
+objects (kernel K5, csrc/otw.cu) with one launch per live frame (or one launch
+for a block of frames).  The single-stream classes in otw_eran.py / livenote_v2.py
+/ livenote.py are this class with n = 1.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+try:
+    from . import _native as nat
+except ImportError:
+    import _native as nat
+
+
+def _pack_refs(refs, device):
+    """refs: list of (12, N_s) arrays or one (n, 12, N) array -> (flat device tensor, lens, offs)."""
+    if isinstance(refs, torch.Tensor):
+        assert refs.dim() == 3 and refs.shape[1] == 12
+        n, _, N = refs.shape
+        flat = refs.to(device=device, dtype=torch.float64).contiguous().reshape(-1)
+        lens = np.full(n, N, dtype=np.int64)
+    else:
+        arrs = [np.ascontiguousarray(r, dtype=np.float64) for r in refs]
+        for r in arrs:
+            if r.ndim != 2 or r.shape[0] != 12:
+                raise nat.AfsError("reference sequences must be (12, frames) (got %r)" % (r.shape,))
+        lens = np.array([r.shape[1] for r in arrs], dtype=np.int64)
+        flat = torch.from_numpy(np.concatenate([r.reshape(-1) for r in arrs])).to(device)
+    offs = np.concatenate(([0], np.cumsum(lens * 12)[:-1])).astype(np.int64)
+    return flat, lens, offs
+
+
+class OtwBatch(object):
+    """n independent online aligners sharing (c, max_run_count, kind, metric)."""
+
+    def __init__(self, refs, c, max_run_count, kind="otw", chroma_diff=False, device=None):
+        nat.require_cuda()
+        self.device = nat.device() if device is None else torch.device(device)
+        self.kind = {"otw": nat.AFS_OTW, "livenote_v2": nat.AFS_LIVENOTE_V2, "livenote": nat.AFS_LIVENOTE_V1}[kind]
+        self.c = int(c)
+        self.max_run_count = int(max_run_count)
+        with torch.cuda.device(self.device):
+            self.d_ref, self.ref_lens, self.ref_offs = _pack_refs(refs, self.device)
+            self.n = int(self.ref_lens.shape[0])
+            L = nat.lib()
+            h = C.c_void_p()
+            nat.check(L.afs_otw_create(C.byref(h), self.kind, self.n, nat.ptr(self.d_ref),
+                                       self.ref_lens.ctypes.data_as(nat._i64p), self.ref_offs.ctypes.data_as(nat._i64p),
+                                       12, self.c, self.max_run_count,
+                                       nat.AFS_COST_EUCLID if chroma_diff else nat.AFS_COST_COSINE))
+            self._h = h
+            nbytes = C.c_size_t()
+            nat.check(L.afs_otw_state_bytes(self._h, C.byref(nbytes)))
+            self.state_bytes = int(nbytes.value)
+            self.state = torch.empty(self.state_bytes, dtype=torch.uint8, device=self.device)
+            self.pts = int(L.afs_otw_points_per_step(self._h))
+            self.reset()
+        off, cap = C.c_int64(), C.c_int64()
+        self.path_off = np.empty(self.n, dtype=np.int64)
+        self.path_cap = np.empty(self.n, dtype=np.int64)
+        for s in range(self.n):
+            nat.check(nat.lib().afs_otw_path_layout(self._h, s, C.byref(off), C.byref(cap)))
+            self.path_off[s], self.path_cap[s] = off.value, cap.value
+        nat.check(nat.lib().afs_otw_path_layout(self._h, -1, C.byref(off), C.byref(cap)))
+        self.path_total = int(cap.value)
+        self._out = {}
+
+    def reset(self):
+        nat.check(nat.lib().afs_otw_reset(self._h, nat.ptr(self.state), nat.stream_ptr()))
+
+    def seed_set_live(self):
+        """State after set_live()'s loop-top best-point call at (0,0) (otw_eran.py:100-108)."""
+        nat.check(nat.lib().afs_otw_seed_set_live(self._h, nat.stream_ptr()))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            nat.lib().afs_otw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _outputs(self, n_frames):
+        if n_frames not in self._out:
+            self._out[n_frames] = (
+                torch.empty((n_frames, self.n), dtype=torch.int32, device=self.device),
+                torch.empty((n_frames, self.n), dtype=torch.int32, device=self.device),
+                torch.empty((n_frames, self.n, self.pts, 2), dtype=torch.int32, device=self.device),
+            )
+        return self._out[n_frames]
+
+    def step_device(self, d_frames, active=None, want_points=True):
+        """d_frames: device tensor (n_frames, n, 12) or (n, 12) float64.  Asynchronous.
+        Returns device tensors (status, npoints, points)."""
+        if d_frames.dim() == 2:
+            d_frames = d_frames.unsqueeze(0)
+        assert d_frames.is_cuda and d_frames.dtype == torch.float64 and d_frames.is_contiguous()
+        assert d_frames.shape[1] == self.n and d_frames.shape[2] == 12
+        nf = int(d_frames.shape[0])
+        st, npts, pts = self._outputs(nf)
+        nat.check(nat.lib().afs_otw_step(self._h, nat.ptr(d_frames), nf, nat.ptr(active), nat.ptr(st), nat.ptr(npts),
+                                         nat.ptr(pts) if want_points else C.c_void_p(0), nat.stream_ptr()))
+        return st, npts, pts
+
+    def insert(self, frames):
+        """Host API: frames (n, 12) array-like -> (status (n,), list of appended points per stream)."""
+        fr = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.float64).reshape(1, self.n, 12)).to(self.device)
+        st, npts, pts = self.step_device(fr)
+        st = st.cpu().numpy()[0]
+        npts = npts.cpu().numpy()[0]
+        pts = pts.cpu().numpy()[0]
+        return st, [[(int(x), int(y)) for x, y in pts[s, : npts[s]]] for s in range(self.n)]
+
+    def _dev_view(self, address, count, dtype):
+        """Wrap `count` int32s at a device address inside the state block as a tensor view."""
+        base = self.state.data_ptr()
+        off = address - base
+        assert 0 <= off and off + count * 4 <= self.state_bytes
+        return self.state[off : off + count * 4].view(dtype)
+
+    def positions(self):
+        p = C.c_void_p()
+        nat.check(nat.lib().afs_otw_positions_ptr(self._h, C.byref(p)))
+        return self._dev_view(p.value, 2 * self.n, torch.int32).cpu().numpy().reshape(self.n, 2)
+
+    def paths(self):
+        """Full device-resident paths as a list of int64 (P,2) arrays."""
+        pp, pl = C.c_void_p(), C.c_void_p()
+        nat.check(nat.lib().afs_otw_path_ptr(self._h, C.byref(pp), C.byref(pl)))
+        lens = self._dev_view(pl.value, self.n, torch.int32).cpu().numpy()
+        flat = self._dev_view(pp.value, 2 * self.path_total, torch.int32).cpu().numpy().reshape(-1, 2)
+        out = []
+        for s in range(self.n):
+            n = int(min(lens[s], self.path_cap[s]))
+            out.append(flat[self.path_off[s] : self.path_off[s] + n].astype(np.int64))
+        return out

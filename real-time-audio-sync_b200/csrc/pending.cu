@@ -5,14 +5,6 @@
 #define AFS_PENDING(name) afs::fail(AFS_ERR_UNSUPPORTED, name ": kernel not implemented yet")
 
 extern "C" {
-int afs_otw_create(afs_otw **, int, int, const double *, const int64_t *, const int64_t *, int, int, int, int) { return AFS_PENDING("afs_otw_create"); }
-int afs_otw_destroy(afs_otw *) { return AFS_OK; }
-int afs_otw_state_bytes(const afs_otw *, size_t *) { return AFS_PENDING("afs_otw_state_bytes"); }
-int afs_otw_reset(afs_otw *, void *, void *) { return AFS_PENDING("afs_otw_reset"); }
-int afs_otw_step(afs_otw *, const double *, int, const uint8_t *, int32_t *, int32_t *, int32_t *, void *) { return AFS_PENDING("afs_otw_step"); }
-int afs_otw_path_layout(const afs_otw *, int, int64_t *, int64_t *) { return AFS_PENDING("afs_otw_path_layout"); }
-int afs_otw_path_ptr(const afs_otw *, const int32_t **, const int32_t **) { return AFS_PENDING("afs_otw_path_ptr"); }
-int afs_otw_positions_ptr(const afs_otw *, const int32_t **) { return AFS_PENDING("afs_otw_positions_ptr"); }
 int afs_chroma_plan_create(afs_chroma_plan **, const double *, int, int, int) { return AFS_PENDING("afs_chroma_plan_create"); }
 int afs_chroma_plan_destroy(afs_chroma_plan *) { return AFS_OK; }
 int64_t afs_chroma_num_frames(const afs_chroma_plan *, int64_t, int) { return AFS_PENDING("afs_chroma_num_frames"); }

@@ -1,0 +1,141 @@
+"""GPU parity: OnlineTimeWarping / LiveNoteV2 / LiveNote through the C ABI (kernel K5)
+vs the reference-generated golden paths and the CPU oracle (bit-exact)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import chroma_like, warped_copy
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def mods(entry):
+    return {n: entry.submodule(n) for n in ("otw_eran", "livenote_v2", "livenote", "batch", "_native")}
+
+
+@pytest.fixture(scope="module")
+def chroma():
+    return np.load(os.path.join(GOLD, "chopin_chroma.npz"))
+
+
+@pytest.fixture(scope="module")
+def paths():
+    return np.load(os.path.join(GOLD, "chopin_paths.npz"))
+
+
+@pytest.fixture(scope="module")
+def syn():
+    return np.load(os.path.join(GOLD, "synth_cases.npz"))
+
+
+def run_insert(obj, live):
+    for i in range(live.shape[1]):
+        if obj.insert(live[:, i]) == "stop":
+            break
+    return np.asarray(obj.path, dtype=np.int64).reshape(-1, 2)
+
+
+@pytest.mark.parametrize("c", [10, 50])
+def test_chopin_insert_loops(mods, chroma, paths, c):
+    ref, live = chroma["ref"], chroma["live"]
+    o = mods["otw_eran"].OnlineTimeWarping(ref, {"c": c, "max_run_count": 3})
+    assert np.array_equal(run_insert(o, live), paths["otw_c%d" % c])
+    assert o.path[0] == (1, 0) and isinstance(o.path, list)
+    o = mods["livenote_v2"].LiveNoteV2(ref, {"search_band_width": c, "max_run_count": 3}, {})
+    assert np.array_equal(run_insert(o, live), paths["ln2_c%d" % c])
+    o = mods["livenote"].LiveNote(ref, {"search_band_width": c, "max_run_count": 3}, {})
+    assert np.array_equal(run_insert(o, live), paths["ln1_c%d" % c])
+
+
+def test_chopin_chroma_diff(mods, chroma, paths):
+    o = mods["livenote_v2"].LiveNoteV2(chroma["dref"], {"search_band_width": 50, "max_run_count": 3}, {}, chroma_diff=True)
+    assert np.array_equal(run_insert(o, chroma["dlive"]), paths["ln2_diff_c50"])
+
+
+@pytest.mark.parametrize("c", [10, 50])
+def test_set_live(mods, chroma, paths, c):
+    o = mods["otw_eran"].OnlineTimeWarping(chroma["ref"], {"c": c, "max_run_count": 3})
+    o.set_live(chroma["live"])
+    assert isinstance(o.path, np.ndarray) and np.array_equal(o.path, paths["otw_setlive_c%d" % c])
+    o = mods["livenote_v2"].LiveNoteV2(chroma["ref"], {"search_band_width": c, "max_run_count": 3}, {})
+    o.set_live(chroma["live"])
+    assert np.array_equal(np.asarray(o.path), paths["ln2_setlive_c%d" % c])
+
+
+def test_synthetic_goldens(mods, syn):
+    r, l = syn["a_ref"], syn["a_live"]
+    OTW, LN2 = mods["otw_eran"].OnlineTimeWarping, mods["livenote_v2"].LiveNoteV2
+    for c in (10, 50):
+        assert np.array_equal(run_insert(OTW(r, {"c": c, "max_run_count": 3}), l), syn["a_otw_c%d" % c])
+        assert np.array_equal(run_insert(LN2(r, {"search_band_width": c, "max_run_count": 3}, {}), l), syn["a_ln2_c%d" % c])
+    assert np.array_equal(run_insert(OTW(r, {"c": 7, "max_run_count": 2}), l), syn["a_otw_c7_r2"])
+    assert np.array_equal(run_insert(LN2(r, {"search_band_width": 33, "max_run_count": 5}, {}), l), syn["a_ln2_c33_r5"])
+    assert np.array_equal(run_insert(OTW(syn["e_b"], {"c": 10, "max_run_count": 3}), syn["e_a"]), syn["e_otw_c10"])
+    assert np.array_equal(run_insert(LN2(syn["e_b"], {"search_band_width": 10, "max_run_count": 3}, {}), syn["e_a"]), syn["e_ln2_c10"])
+
+
+def test_stop_and_positions(mods, syn):
+    o = mods["otw_eran"].OnlineTimeWarping(syn["a_ref"], {"c": 20, "max_run_count": 3})
+    live = syn["a_live_long"]
+    stopped_at = None
+    for i in range(live.shape[1]):
+        if o.insert(live[:, i]) == "stop":
+            stopped_at = i
+            break
+    assert stopped_at is not None
+    assert np.array_equal(np.asarray(o.path), syn["a_otw_long_c20"])
+    assert [o.t, o.j] == syn["a_otw_long_tj"].tolist()
+    assert o.insert(live[:, 0]) == "stop"          # finished objects stay finished
+
+
+def test_c500_batched_many_frames_per_launch(mods, syn):
+    """BASELINE cfg[3] band (c = 500): whole live sequence in one launch, two kinds."""
+    r, l = syn["c500_ref"], syn["c500_live"]
+    import torch
+    for kind, key in (("otw", "c500_otw"), ("livenote_v2", "c500_ln2")):
+        b = mods["batch"].OtwBatch([r, r, r], 500, 3, kind=kind)
+        frames = torch.from_numpy(np.ascontiguousarray(np.repeat(l.T[:, None, :], 3, axis=1))).cuda()
+        st, npts, pts = b.step_device(frames)
+        got = b.paths()
+        for s in range(3):
+            assert np.array_equal(got[s], syn[key]), (kind, s)
+        # per-step outputs agree with the device-resident path
+        npts = npts.cpu().numpy()
+        pts = pts.cpu().numpy()
+        flat = np.concatenate([pts[f, 0, : npts[f, 0]] for f in range(frames.shape[0])])
+        assert np.array_equal(flat, syn[key])
+        b.close()
+
+
+def test_ragged_batch_vs_oracle(mods, orc):
+    """Streams with different reference lengths and an inactive-stream mask."""
+    rng = np.random.default_rng(9)
+    refs = [chroma_like(rng, n) for n in (120, 333, 64, 250)]
+    lives = [warped_copy(rng, r, 300) for r in refs]
+    import torch
+    b = mods["batch"].OtwBatch(refs, 25, 3, kind="otw")
+    oracles = [orc.OnlineTimeWarping(r, {"c": 25, "max_run_count": 3}) for r in refs]
+    done = [False] * 4
+    active = torch.ones(4, dtype=torch.uint8, device="cuda")
+    for k in range(300):
+        if k == 100:
+            active[1] = 0                      # pause stream 1 for 50 steps
+        if k == 150:
+            active[1] = 1
+        fr = np.stack([lv[:, k] for lv in lives])
+        st, _, _ = b.step_device(torch.from_numpy(fr).cuda().reshape(1, 4, 12), active=active)
+        st = st.cpu().numpy()[0]
+        for s in range(4):
+            if s == 1 and 100 <= k < 150:
+                continue
+            if not done[s]:
+                r = oracles[s].insert(lives[s][:, k])
+                assert (r == "stop") == (st[s] == 1), (k, s)
+                done[s] = r == "stop"
+    got = b.paths()
+    for s in range(4):
+        assert np.array_equal(got[s], oracles[s].path_array()), s
+    b.close()
