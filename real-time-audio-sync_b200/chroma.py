@@ -1,0 +1,193 @@
+"""Drop-in for the reference's ``chroma.py``.
+
+Reference: chroma.py:20-90 — ``wav_to_chroma(path)``, ``wav_to_chroma_col(buf)``,
+``create_stft`` + ``create_chroma`` and ``wav_to_chroma_diff(path)``; globals ``fft_len``,
+``hop_size``, ``fs``.  Framing, Hann window, real FFT, |X|^2, the 12 x 2049 filterbank
+and the L2 normalisation run fused in kernel K1 (csrc/chroma.cu) through
+``afs_chroma_batch``; WAV decoding stays on the CPU (it only feeds samples).
+
+Differences from the reference, all explicit:
+* ``create_stft`` is not exposed on its own — the spectrum never leaves the SM; use
+  ``wav_samples_to_chroma`` / ``chroma_batch`` (or ``create_chroma(create_stft(wav))``,
+  where ``create_stft`` returns a lazy handle that ``create_chroma`` consumes);
+* arithmetic is float32 by default (<= 1e-6 abs from the float64 reference on real
+  audio); ``compute="fp64"`` runs the same kernel in float64;
+* ``librosa.load`` is replaced by a WAV reader for 22 050 Hz PCM16 files (no resampler).
+"""
+import ctypes as C
+import wave
+
+import numpy as np
+import torch
+
+try:
+    from . import _native as nat
+except ImportError:
+    import _native as nat
+
+# globals (chroma.py:20-22)
+fft_len = 4096
+hop_size = 2048
+fs = 22050
+
+
+def chroma_filterbank(sr=fs, n_fft=fft_len, n_chroma=12, A440=440.0, ctroct=5.0, octwidth=2.0):
+    """librosa.filters.chroma(sr, n_fft) with its defaults (chroma.py:69): (12, 1 + n_fft/2) float64.
+    Host-side, computed once; the kernel consumes it through afs_chroma_plan_create."""
+    freqs = np.linspace(0, sr, n_fft, endpoint=False)[1:]
+    bins = n_chroma * np.log2(freqs / (float(A440) / 16.0))
+    bins = np.concatenate(([bins[0] - 1.5 * n_chroma], bins))
+    width = np.concatenate((np.maximum(bins[1:] - bins[:-1], 1.0), [1.0]))
+    D = np.subtract.outer(bins, np.arange(0, n_chroma, dtype="d")).T
+    half = np.round(float(n_chroma) / 2)
+    D = np.remainder(D + half + 10 * n_chroma, n_chroma) - half
+    wts = np.exp(-0.5 * (2 * D / np.tile(width, (n_chroma, 1))) ** 2)
+    wts = wts / np.sqrt(np.sum(wts ** 2, axis=0, keepdims=True))
+    wts *= np.tile(np.exp(-0.5 * (((bins / n_chroma - ctroct) / octwidth) ** 2)), (n_chroma, 1))
+    wts = np.roll(wts, -3 * (n_chroma // 12), axis=0)
+    return np.ascontiguousarray(wts[:, : int(1 + n_fft / 2)])
+
+
+class ChromaPlan(object):
+    """Device tables (window, twiddles, filterbank) for one (n_fft, hop) configuration."""
+
+    def __init__(self, n_fft=fft_len, hop=hop_size, filterbank=None, device=None):
+        nat.require_cuda()
+        self.device = nat.device() if device is None else torch.device(device)
+        self.n_fft, self.hop = int(n_fft), int(hop)
+        fb = chroma_filterbank(fs, n_fft) if filterbank is None else np.ascontiguousarray(filterbank, dtype=np.float64)
+        assert fb.shape == (12, 1 + n_fft // 2)
+        self.filterbank = fb
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().afs_chroma_plan_create(C.byref(h), C.c_void_p(fb.ctypes.data), self.n_fft, self.hop, 12))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            nat.lib().afs_chroma_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def num_frames(self, n_samples, center=True):
+        return int(nat.lib().afs_chroma_num_frames(self._h, int(n_samples), 1 if center else 0))
+
+    def run(self, d_audio, offsets, d_out=None, center=True, normalize=True, out_dtype=torch.float32, compute="fp32",
+            out_offsets=None):
+        """K1 on the current stream.  d_audio: float32 device tensor holding all tracks;
+        offsets: (n_tracks+1) sample offsets.  Returns (d_out, frame_offsets): track k's chroma
+        is d_out[12*frame_offsets[k] : 12*frame_offsets[k+1]].view(12, frames_k)."""
+        assert d_audio.is_cuda and d_audio.dtype == torch.float32
+        offs = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offs.shape[0] - 1
+        frames = np.array([self.num_frames(offs[k + 1] - offs[k], center) for k in range(n)], dtype=np.int64)
+        foffs = np.concatenate(([0], np.cumsum(frames))).astype(np.int64)
+        if d_out is None:
+            d_out = torch.empty(int(12 * foffs[-1]), dtype=out_dtype, device=d_audio.device)
+        oo = None if out_offsets is None else np.ascontiguousarray(out_offsets, dtype=np.int64)
+        nat.check(nat.lib().afs_chroma_batch(
+            self._h, nat.ptr(d_audio), offs.ctypes.data_as(nat._i64p), n, 1 if center else 0, 1 if normalize else 0,
+            nat.ptr(d_out), None if oo is None else oo.ctypes.data_as(nat._i64p),
+            nat.AFS_F64 if d_out.dtype == torch.float64 else nat.AFS_F32,
+            nat.AFS_F64 if compute in ("fp64", "f64") else nat.AFS_F32, nat.stream_ptr()))
+        return d_out, foffs
+
+
+_default_plan = None
+
+
+def default_plan():
+    global _default_plan
+    if _default_plan is None:
+        _default_plan = ChromaPlan(fft_len, hop_size)
+    return _default_plan
+
+
+def chroma_batch(tracks, center=True, normalize=True, compute="fp32"):
+    """Many tracks in one launch: list of 1-D sample arrays -> list of (12, frames) float64 arrays."""
+    plan = default_plan()
+    lens = [len(t) + (len(t) & 1) for t in tracks]                 # even offsets (8-byte aligned float2 loads)
+    offs = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    flat = np.zeros(int(offs[-1]), dtype=np.float32)
+    ends = []
+    for k, t in enumerate(tracks):
+        flat[offs[k] : offs[k] + len(t)] = np.asarray(t, dtype=np.float32)
+        ends.append(offs[k] + len(t))
+    # padded sample (if any) must not create an extra frame: pass true ends through per-track offsets
+    d_audio = torch.from_numpy(flat).to(plan.device)
+    outs = []
+    # tracks whose length is odd would see one padding zero; frames are counted on the true length
+    true_offs = offs.copy()
+    d_out, foffs = plan.run(d_audio, true_offs, center=center, normalize=normalize, out_dtype=torch.float64, compute=compute)
+    host = d_out.cpu().numpy()
+    for k, t in enumerate(tracks):
+        nfr = plan.num_frames(len(t), center)
+        blk = host[12 * foffs[k] : 12 * foffs[k + 1]].reshape(12, -1)
+        outs.append(np.ascontiguousarray(blk[:, :nfr]))
+    return outs
+
+
+def wav_samples_to_chroma(wav, normalize=True, compute="fp32"):
+    """create_chroma(create_stft(wav)) (chroma.py:31-33) -> (12, M) float64."""
+    return chroma_batch([np.asarray(wav)], center=True, normalize=normalize, compute=compute)[0]
+
+
+def load_wav(path_to_wav):
+    """Stand-in for librosa.load(path) defaults (mono float32 at 22 050 Hz) for PCM16 WAVs; CPU only."""
+    with wave.open(path_to_wav, "rb") as w:
+        rate, nch, width = w.getframerate(), w.getnchannels(), w.getsampwidth()
+        raw = w.readframes(w.getnframes())
+    if width != 2:
+        raise ValueError("only PCM16 WAV files are supported")
+    x = np.frombuffer(raw, dtype="<i2").astype(np.float32) / np.float32(32768.0)
+    if nch > 1:
+        x = x.reshape(-1, nch).mean(axis=1, dtype=np.float32)
+    return np.ascontiguousarray(x), rate
+
+
+def wav_to_chroma(path_to_wav):
+    """chroma.py:25-33."""
+    wav, wav_fs = load_wav(path_to_wav)
+    assert(wav_fs == 22050)
+    return wav_samples_to_chroma(wav)
+
+
+def wav_to_chroma_col(wav_buf, compute="fp32"):
+    """chroma.py:35-42: one un-padded 4096-sample frame -> (12,)."""
+    assert(len(wav_buf) == fft_len)
+    return chroma_batch([np.asarray(wav_buf)], center=False, compute=compute)[0][:, 0]
+
+
+class _LazyStft(object):
+    """What create_stft returns here: the samples, to be consumed by create_chroma
+    (the spectrum itself is never materialised on the GPU path)."""
+
+    def __init__(self, wav):
+        self.wav = np.asarray(wav)
+
+
+def create_stft(wav):
+    """chroma.py:44-65 (lazy: see module docstring)."""
+    return _LazyStft(wav)
+
+
+def create_chroma(ft, normalize=True):
+    """chroma.py:67-75 for the handle returned by create_stft."""
+    if not isinstance(ft, _LazyStft):
+        raise nat.AfsError("create_chroma expects the handle returned by create_stft (spectra are not materialised)")
+    return wav_samples_to_chroma(ft.wav, normalize=normalize)
+
+
+def chroma_to_diff(chroma):
+    """chroma.py:88-90 on an existing chromagram: half-wave-rectified time difference."""
+    return np.clip(np.diff(chroma), 0, float('inf'))
+
+
+def wav_to_chroma_diff(path_to_wav):
+    """chroma.py:77-90."""
+    return chroma_to_diff(wav_to_chroma(path_to_wav))

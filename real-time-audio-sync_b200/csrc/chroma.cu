@@ -1,0 +1,408 @@
+// K1 — fused framing + Hann + real FFT-4096 + |X|^2 + 12 x 2049 chroma filterbank + L2
+// normalisation, batched over tracks, on sm_100a.
+//
+// Replaces chroma.create_stft + chroma.create_chroma (reference chroma.py:44-75; the
+// same code inlined in wtw.py:137-160 and :37-41) and the single-frame
+// chroma.wav_to_chroma_col (chroma.py:35-42 == wtw.py:82-90).
+//
+// One CTA of 128 threads transforms one frame at a time (persistent grid-stride loop
+// over all frames of all tracks; neighbouring CTAs work on neighbouring frames, so the
+// 50 %-overlapping half of each frame is an L2 hit and every sample crosses HBM once).
+// The real 4096-point FFT is a packed 2048-point complex FFT  z[n] = x[2n] + i x[2n+1]
+// decomposed 2048 = 16 x 16 x 8 (three register-resident radix passes, two shared-memory
+// exchanges), followed by the real-FFT untangle, |X|^2, the filterbank and the norm —
+// nothing but the 12 chroma values per frame is written back.
+#include <math_constants.h>
+
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+#include "afs_common.cuh"
+
+namespace {
+
+constexpr int kNfft = 4096;
+constexpr int kNc = 2048;          // packed complex length
+constexpr int kBins = 2049;
+constexpr int kChroma = 12;
+constexpr int kThreads = 128;
+constexpr int kStrideA = 136;      // [k1][m] row stride (complex), padded: 2-wavefront 64-bit access
+constexpr int kStrideB = 130;      // [k1][k2*8+m2] row stride (complex), padded for 128-bit reads
+
+template <typename T> struct Cx { T x, y; };
+
+template <typename T> __device__ __forceinline__ Cx<T> cadd(Cx<T> a, Cx<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T> __device__ __forceinline__ Cx<T> csub(Cx<T> a, Cx<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T> __device__ __forceinline__ Cx<T> cmul(Cx<T> a, Cx<T> b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+template <typename T> __device__ __forceinline__ Cx<T> mul_mi(Cx<T> a) { return {a.y, -a.x}; }   // a * (-i)
+
+// natural-order 4-point DFT (forward, e^{-2 pi i nk/4})
+template <typename T> __device__ __forceinline__ void fft4(Cx<T> &a, Cx<T> &b, Cx<T> &c, Cx<T> &d)
+{
+    const Cx<T> s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = mul_mi(csub(b, d));
+    a = cadd(s0, s2);
+    b = cadd(s1, s3);
+    c = csub(s0, s2);
+    d = csub(s1, s3);
+}
+
+// natural-order 16-point DFT in registers: 16 = 4 x 4
+template <typename T> __device__ __forceinline__ void fft16(Cx<T> (&v)[16])
+{
+    constexpr T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173;   // cos/sin(pi/8)
+    constexpr T r2 = (T)0.70710678118654752440;
+#pragma unroll
+    for (int n2 = 0; n2 < 4; n2++) fft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+    // v[4*k1 + n2] now holds t[n2][k1]; multiply by W16^(n2*k1)
+    v[4 * 1 + 1] = cmul(v[4 * 1 + 1], Cx<T>{c1, -s1});     // W16^1
+    v[4 * 1 + 2] = cmul(v[4 * 1 + 2], Cx<T>{r2, -r2});     // W16^2
+    v[4 * 1 + 3] = cmul(v[4 * 1 + 3], Cx<T>{s1, -c1});     // W16^3
+    v[4 * 2 + 1] = cmul(v[4 * 2 + 1], Cx<T>{r2, -r2});     // W16^2
+    v[4 * 2 + 2] = mul_mi(v[4 * 2 + 2]);                   // W16^4
+    v[4 * 2 + 3] = cmul(v[4 * 2 + 3], Cx<T>{-r2, -r2});    // W16^6
+    v[4 * 3 + 1] = cmul(v[4 * 3 + 1], Cx<T>{s1, -c1});     // W16^3
+    v[4 * 3 + 2] = cmul(v[4 * 3 + 2], Cx<T>{-r2, -r2});    // W16^6
+    v[4 * 3 + 3] = cmul(v[4 * 3 + 3], Cx<T>{-c1, s1});     // W16^9
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) fft4(v[4 * k1 + 0], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+    // v[4*k1 + k2] = X[k1 + 4*k2]  -> reorder to natural
+    Cx<T> o[16];
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++)
+#pragma unroll
+        for (int k2 = 0; k2 < 4; k2++) o[k1 + 4 * k2] = v[4 * k1 + k2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = o[i];
+}
+
+// natural-order 8-point DFT: 8 = 4 x 2
+template <typename T> __device__ __forceinline__ void fft8(Cx<T> (&v)[8])
+{
+    constexpr T r2 = (T)0.70710678118654752440;
+    fft4(v[0], v[2], v[4], v[6]);      // t[0][k1] in v[0],v[2],v[4],v[6]
+    fft4(v[1], v[3], v[5], v[7]);      // t[1][k1]
+    v[3] = cmul(v[3], Cx<T>{r2, -r2}); // W8^1
+    v[5] = mul_mi(v[5]);               // W8^2
+    v[7] = cmul(v[7], Cx<T>{-r2, -r2});// W8^3
+    Cx<T> o[8];
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) {
+        o[k1] = cadd(v[2 * k1], v[2 * k1 + 1]);
+        o[k1 + 4] = csub(v[2 * k1], v[2 * k1 + 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = o[i];
+}
+
+template <typename T>
+struct ChromaTables {
+    const T *hann;          // 4096
+    const Cx<T> *tw2048;    // exp(-2 pi i j / 2048), j < 2048
+    const Cx<T> *tw4096;    // exp(-2 pi i k / 4096), k <= 1024
+    const T *fb;            // [2049][12]
+};
+
+struct ChromaBatch {
+    const float *audio;
+    const int64_t *sample_off;   // n_tracks + 1
+    const int64_t *frame_off;    // n_tracks + 1 (prefix of frames per track)
+    const int64_t *out_off;      // n_tracks (frames), output placement
+    int n_tracks;
+    int64_t total_frames;
+    int hop, center_pad, normalize, out_f64;
+    void *out;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) chroma_kernel(const ChromaTables<T> tb, const ChromaBatch bt)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    Cx<T> *sA = reinterpret_cast<Cx<T> *>(s_raw);          // 16 x kStrideA   (later: Z natural, 2048)
+    Cx<T> *sB = sA + 16 * kStrideA;                        // 16 x kStrideB
+    T *sRed = reinterpret_cast<T *>(sB + 16 * kStrideB);   // 4 warps x 12
+    const int t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
+
+    for (int64_t f = blockIdx.x; f < bt.total_frames; f += gridDim.x) {
+        // ---- locate (track, frame) ----
+        int lo = 0, hi = bt.n_tracks;            // frame_off[lo] <= f < frame_off[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (bt.frame_off[mid] <= f) lo = mid; else hi = mid;
+        }
+        const int track = lo;
+        const int64_t m_idx = f - bt.frame_off[track];
+        const int64_t s_begin = bt.sample_off[track];
+        const int64_t n_samp = bt.sample_off[track + 1] - s_begin;
+        const int64_t frames_k = bt.frame_off[track + 1] - bt.frame_off[track];
+        const int64_t start = m_idx * bt.hop - (bt.center_pad ? kNfft / 2 : 0);     // chroma.py:49 left zero pad
+        const float *x = bt.audio + s_begin;
+
+        // ---- pass 1: thread m = t, n1 = 0..15: z[128 n1 + m] = x[256 n1 + 2m] + i x[256 n1 + 2m + 1], windowed ----
+        Cx<T> v[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            const int n = 256 * n1 + 2 * t;
+            const int64_t s = start + n;
+            float2 xv = make_float2(0.f, 0.f);
+            if (s >= 0 && s + 1 < n_samp) xv = __ldg(reinterpret_cast<const float2 *>(x + s));
+            else {
+                if (s >= 0 && s < n_samp) xv.x = __ldg(x + s);
+                if (s + 1 >= 0 && s + 1 < n_samp) xv.y = __ldg(x + s + 1);
+            }
+            v[n1].x = (T)xv.x * __ldg(tb.hann + n);          // chroma.py:62 section * np.hanning
+            v[n1].y = (T)xv.y * __ldg(tb.hann + n + 1);
+        }
+        fft16(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) {
+            Cx<T> y = v[k1];
+            if (k1 > 0) y = cmul(y, tb.tw2048[t * k1]);                // W_2048^(m k1)
+            sA[k1 * kStrideA + t] = y;
+        }
+        __syncthreads();
+        // ---- pass 2: thread (k1 = t / 8, m2 = t % 8): u[m1] = A[k1][8 m1 + m2] ----
+        {
+            const int k1 = t >> 3, m2 = t & 7;
+#pragma unroll
+            for (int m1 = 0; m1 < 16; m1++) v[m1] = sA[k1 * kStrideA + 8 * m1 + m2];
+            fft16(v);
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) {
+                Cx<T> y = v[k2];
+                if (k2 > 0) y = cmul(y, tb.tw2048[16 * m2 * k2]);      // W_128^(m2 k2)
+                sB[k1 * kStrideB + k2 * 8 + m2] = y;
+            }
+        }
+        __syncthreads();
+        // ---- pass 3: two (k1, k2) groups per thread; 8-point DFT over m2 -> Z[k1 + 16 k2 + 256 k3] ----
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int p = t + h * kThreads;        // p = k2 * 16 + k1  (lanes run along k1)
+            const int k1 = p & 15, k2 = p >> 4;
+            Cx<T> u[8];
+#pragma unroll
+            for (int m2 = 0; m2 < 8; m2++) u[m2] = sB[k1 * kStrideB + k2 * 8 + m2];
+            fft8(u);
+#pragma unroll
+            for (int k3 = 0; k3 < 8; k3++) sA[k1 + 16 * k2 + 256 * k3] = u[k3];
+        }
+        __syncthreads();
+        // ---- untangle + power + filterbank ----
+        T acc[kChroma];
+#pragma unroll
+        for (int c = 0; c < kChroma; c++) acc[c] = (T)0;
+        auto add_bin = [&](int k, T p) {
+            const T *w = tb.fb + (size_t)k * kChroma;
+#pragma unroll
+            for (int c = 0; c < kChroma; c++) acc[c] = fma(__ldg(w + c), p, acc[c]);
+        };
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int k = t + kThreads * i;            // 0 .. 1023
+            if (k == 0) {
+                const Cx<T> z0 = sA[0];
+                const T x0 = z0.x + z0.y, xn = z0.x - z0.y;       // X[0], X[2048] (real)
+                add_bin(0, x0 * x0);
+                add_bin(2048, xn * xn);
+                const Cx<T> zq = sA[1024];                        // X[1024] = conj(Z[1024])
+                add_bin(1024, zq.x * zq.x + zq.y * zq.y);
+            } else {
+                const Cx<T> zk = sA[k], zn = sA[kNc - k];
+                const Cx<T> e = {(T)0.5 * (zk.x + zn.x), (T)0.5 * (zk.y - zn.y)};     // (Zk + conj Zn)/2
+                const Cx<T> d = {(T)0.5 * (zk.x - zn.x), (T)0.5 * (zk.y + zn.y)};     // (Zk - conj Zn)/2
+                const Cx<T> wk = tb.tw4096[k];
+                const Cx<T> o = mul_mi(cmul(wk, d));                                  // -i w_k d
+                const Cx<T> xa = cadd(e, o), xb = csub(e, o);                         // X[k], conj X[2048-k]
+                add_bin(k, xa.x * xa.x + xa.y * xa.y);                                // chroma.py:68 abs(ft)**2
+                add_bin(kNc - k, xb.x * xb.x + xb.y * xb.y);
+            }
+        }
+        // ---- block reduction of the 12 partial sums (chroma.py:70 np.dot(chromafb, spec)) ----
+#pragma unroll
+        for (int c = 0; c < kChroma; c++) {
+            T a = acc[c];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+            acc[c] = a;
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < kChroma; c++) sRed[warp * kChroma + c] = acc[c];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int c = lane < kChroma ? lane : 0;
+            T raw = sRed[c] + sRed[kChroma + c] + sRed[2 * kChroma + c] + sRed[3 * kChroma + c];
+            if (lane >= kChroma) raw = (T)0;
+            T val = raw;
+            if (bt.normalize) {
+                // librosa.util.normalize(norm=2, axis=0): chroma.py:74; tiny lengths -> 1
+                T ss = raw * raw;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+                T len = sqrt(ss);
+                const T tiny = sizeof(T) == 4 ? (T)FLT_MIN : (T)DBL_MIN;
+                if (len < tiny) len = (T)1;
+                val = raw / len;
+            }
+            if (lane < kChroma) {
+                const int64_t o = kChroma * bt.out_off[track] + (int64_t)lane * frames_k + m_idx;
+                if (bt.out_f64) static_cast<double *>(bt.out)[o] = (double)val;
+                else static_cast<float *>(bt.out)[o] = (float)val;
+            }
+        }
+        __syncthreads();      // sRed / sA reused by the next frame
+    }
+}
+
+}  // namespace
+
+struct afs_chroma_plan {
+    int n_fft = kNfft, hop = 2048;
+    // device tables (float and double variants)
+    float *f_hann = nullptr, *f_fb = nullptr;
+    Cx<float> *f_tw2048 = nullptr, *f_tw4096 = nullptr;
+    double *d_hann = nullptr, *d_fb = nullptr;
+    Cx<double> *d_tw2048 = nullptr, *d_tw4096 = nullptr;
+    int64_t *d_meta = nullptr;     // sample_off | frame_off | out_off
+    int meta_cap = 0;
+};
+
+template <typename T> static size_t chroma_smem_bytes()
+{
+    return sizeof(Cx<T>) * (16 * kStrideA + 16 * kStrideB) + sizeof(T) * 4 * kChroma;
+}
+
+template <typename T>
+static int upload(T **dst, const std::vector<T> &src)
+{
+    AFS_CUDA(cudaMalloc(dst, sizeof(T) * src.size()));
+    AFS_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+    return AFS_OK;
+}
+
+extern "C" {
+
+int afs_chroma_plan_create(afs_chroma_plan **out, const double *h_filterbank, int n_fft, int hop, int n_chroma)
+{
+    if (!out || !h_filterbank) return afs::fail(AFS_ERR_INVALID, "afs_chroma_plan_create: null argument");
+    if (n_fft != kNfft || n_chroma != kChroma)
+        return afs::fail(AFS_ERR_UNSUPPORTED, "afs_chroma: only n_fft = 4096 and 12 chroma bins are implemented (got %d, %d)", n_fft, n_chroma);
+    if (hop <= 0 || hop > n_fft || (hop & 1)) return afs::fail(AFS_ERR_INVALID, "afs_chroma: hop must be even and in (0, n_fft]");
+    afs_chroma_plan *pl = new afs_chroma_plan();
+    pl->hop = hop;
+    const double pi = 3.14159265358979323846;
+    std::vector<double> hann(kNfft), fb((size_t)kBins * kChroma);
+    std::vector<Cx<double>> t2(kNc), t4(1025);
+    for (int n = 0; n < kNfft; n++) hann[n] = 0.5 - 0.5 * std::cos(2.0 * pi * n / (kNfft - 1));   // np.hanning (symmetric)
+    for (int j = 0; j < kNc; j++) t2[j] = {std::cos(2.0 * pi * j / kNc), -std::sin(2.0 * pi * j / kNc)};
+    for (int k = 0; k <= 1024; k++) t4[k] = {std::cos(2.0 * pi * k / kNfft), -std::sin(2.0 * pi * k / kNfft)};
+    for (int c = 0; c < kChroma; c++)
+        for (int k = 0; k < kBins; k++) fb[(size_t)k * kChroma + c] = h_filterbank[(size_t)c * kBins + k];
+    std::vector<float> hannf(hann.begin(), hann.end()), fbf(fb.begin(), fb.end());
+    std::vector<Cx<float>> t2f(kNc), t4f(1025);
+    for (int j = 0; j < kNc; j++) t2f[j] = {(float)t2[j].x, (float)t2[j].y};
+    for (int k = 0; k <= 1024; k++) t4f[k] = {(float)t4[k].x, (float)t4[k].y};
+    int rc = AFS_OK;
+    if ((rc = upload(&pl->d_hann, hann)) || (rc = upload(&pl->d_fb, fb)) || (rc = upload(&pl->d_tw2048, t2)) ||
+        (rc = upload(&pl->d_tw4096, t4)) || (rc = upload(&pl->f_hann, hannf)) || (rc = upload(&pl->f_fb, fbf)) ||
+        (rc = upload(&pl->f_tw2048, t2f)) || (rc = upload(&pl->f_tw4096, t4f))) {
+        afs_chroma_plan_destroy(pl);
+        return rc;
+    }
+    cudaError_t e = cudaFuncSetAttribute(chroma_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chroma_smem_bytes<double>());
+    if (e != cudaSuccess) {
+        afs_chroma_plan_destroy(pl);
+        return afs::fail(AFS_ERR_CUDA, "afs_chroma_plan_create: %s", cudaGetErrorString(e));
+    }
+    *out = pl;
+    return AFS_OK;
+}
+
+int afs_chroma_plan_destroy(afs_chroma_plan *pl)
+{
+    if (!pl) return AFS_OK;
+    cudaFree(pl->f_hann); cudaFree(pl->f_fb); cudaFree(pl->f_tw2048); cudaFree(pl->f_tw4096);
+    cudaFree(pl->d_hann); cudaFree(pl->d_fb); cudaFree(pl->d_tw2048); cudaFree(pl->d_tw4096);
+    cudaFree(pl->d_meta);
+    delete pl;
+    return AFS_OK;
+}
+
+int64_t afs_chroma_num_frames(const afs_chroma_plan *pl, int64_t n_samples, int center_pad)
+{
+    if (!pl || n_samples < 0) return 0;
+    // chroma.py:49-54: x = [zeros(L/2), wav]; num_hops = floor((len(x) - L) / H) + 1
+    const int64_t n = n_samples + (center_pad ? pl->n_fft / 2 : 0);
+    if (n < pl->n_fft) return 0;
+    return (n - pl->n_fft) / pl->hop + 1;
+}
+
+}  // extern "C"
+
+template <typename T>
+static int launch_chroma(const ChromaTables<T> &tb, const ChromaBatch &bt, cudaStream_t st)
+{
+    const size_t smem = chroma_smem_bytes<T>();
+    int occ = 0;
+    AFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chroma_kernel<T>, kThreads, smem));
+    if (occ < 1) return afs::fail(AFS_ERR_CUDA, "chroma kernel does not fit on an SM");
+    int64_t blocks = (int64_t)afs::sm_count() * occ;
+    if (blocks > bt.total_frames) blocks = bt.total_frames;
+    chroma_kernel<T><<<(unsigned)blocks, kThreads, smem, st>>>(tb, bt);
+    afs::count_launch();
+    AFS_CUDA(cudaGetLastError());
+    return AFS_OK;
+}
+
+extern "C" int afs_chroma_batch(afs_chroma_plan *pl, const float *d_audio, const int64_t *h_offsets, int n_tracks,
+                                int center_pad, int normalize, void *d_out, const int64_t *h_out_offsets, int out_dtype,
+                                int compute_dtype, void *stream)
+{
+    if (!pl || !d_audio || !h_offsets || !d_out || n_tracks <= 0)
+        return afs::fail(AFS_ERR_INVALID, "afs_chroma_batch: null argument or n_tracks <= 0");
+    if ((out_dtype != AFS_F32 && out_dtype != AFS_F64) || (compute_dtype != AFS_F32 && compute_dtype != AFS_F64))
+        return afs::fail(AFS_ERR_INVALID, "afs_chroma_batch: bad dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<int64_t> meta((size_t)3 * n_tracks + 2);
+    int64_t *s_off = meta.data(), *f_off = s_off + n_tracks + 1, *o_off = f_off + n_tracks + 1;
+    f_off[0] = 0;
+    for (int k = 0; k < n_tracks; k++) {
+        if (h_offsets[k + 1] < h_offsets[k]) return afs::fail(AFS_ERR_INVALID, "afs_chroma_batch: offsets must be non-decreasing");
+        if (h_offsets[k] & 1) return afs::fail(AFS_ERR_INVALID, "afs_chroma_batch: track offsets must be even (8-byte aligned samples)");
+        s_off[k] = h_offsets[k];
+        f_off[k + 1] = f_off[k] + afs_chroma_num_frames(pl, h_offsets[k + 1] - h_offsets[k], center_pad);
+        o_off[k] = h_out_offsets ? h_out_offsets[k] : f_off[k];
+    }
+    s_off[n_tracks] = h_offsets[n_tracks];
+    const int64_t total = f_off[n_tracks];
+    if (total == 0) return AFS_OK;
+    if (pl->meta_cap < (int)meta.size()) {
+        cudaFree(pl->d_meta);
+        pl->d_meta = nullptr;
+        AFS_CUDA(cudaMalloc(&pl->d_meta, sizeof(int64_t) * meta.size()));
+        pl->meta_cap = (int)meta.size();
+    }
+    // pageable source: the copy is staged before the call returns, so `meta` may go out of scope
+    AFS_CUDA(cudaMemcpyAsync(pl->d_meta, meta.data(), sizeof(int64_t) * meta.size(), cudaMemcpyHostToDevice, st));
+    ChromaBatch bt;
+    bt.audio = d_audio;
+    bt.sample_off = pl->d_meta;
+    bt.frame_off = pl->d_meta + n_tracks + 1;
+    bt.out_off = pl->d_meta + 2 * (n_tracks + 1);
+    bt.n_tracks = n_tracks;
+    bt.total_frames = total;
+    bt.hop = pl->hop;
+    bt.center_pad = center_pad;
+    bt.normalize = normalize;
+    bt.out_f64 = out_dtype == AFS_F64;
+    bt.out = d_out;
+    if (compute_dtype == AFS_F32) {
+        ChromaTables<float> tb{pl->f_hann, pl->f_tw2048, pl->f_tw4096, pl->f_fb};
+        return launch_chroma<float>(tb, bt, st);
+    }
+    ChromaTables<double> tb{pl->d_hann, pl->d_tw2048, pl->d_tw4096, pl->d_fb};
+    return launch_chroma<double>(tb, bt, st);
+}

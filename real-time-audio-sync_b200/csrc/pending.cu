@@ -5,10 +5,6 @@
 #define AFS_PENDING(name) afs::fail(AFS_ERR_UNSUPPORTED, name ": kernel not implemented yet")
 
 extern "C" {
-int afs_chroma_plan_create(afs_chroma_plan **, const double *, int, int, int) { return AFS_PENDING("afs_chroma_plan_create"); }
-int afs_chroma_plan_destroy(afs_chroma_plan *) { return AFS_OK; }
-int64_t afs_chroma_num_frames(const afs_chroma_plan *, int64_t, int) { return AFS_PENDING("afs_chroma_num_frames"); }
-int afs_chroma_batch(afs_chroma_plan *, const float *, const int64_t *, int, int, int, void *, const int64_t *, int, int, void *) { return AFS_PENDING("afs_chroma_batch"); }
 int afs_wtw_create(afs_wtw **, int, const double *, const int64_t *, const int64_t *, int, int, int) { return AFS_PENDING("afs_wtw_create"); }
 int afs_wtw_destroy(afs_wtw *) { return AFS_OK; }
 int afs_wtw_state_bytes(const afs_wtw *, size_t *) { return AFS_PENDING("afs_wtw_state_bytes"); }

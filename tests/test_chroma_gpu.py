@@ -1,0 +1,93 @@
+"""GPU parity: fused STFT->chroma kernel (K1) vs the reference's own chroma (golden
+vectors generated from chroma.py) and the numpy oracle.  Tolerance from
+BASELINE.json north_star: 1e-4 absolute (float32 compute); float64 compute mode 1e-9."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL_F32 = 1e-4
+TOL_F64 = 1e-9
+
+
+@pytest.fixture(scope="module")
+def chroma(entry):
+    return entry.submodule("chroma")
+
+
+@pytest.fixture(scope="module")
+def audio():
+    aud = np.load(os.path.join(GOLD, "audio_15s.npz"))
+    out = {}
+    for tag in ("ref", "live"):
+        st = aud[tag + "_i16"]
+        out[tag] = (st.astype(np.float32) / np.float32(32768.0)).mean(axis=1, dtype=np.float32)
+        out[tag + "_chroma"] = aud[tag + "_chroma"]
+        out[tag + "_raw"] = aud[tag + "_raw_chroma"]
+        out[tag + "_cols"] = aud[tag + "_cols"]
+    return out
+
+
+@pytest.mark.parametrize("tag", ["ref", "live"])
+def test_real_audio_vs_reference_golden(chroma, audio, tag):
+    got = chroma.wav_samples_to_chroma(audio[tag])
+    want = audio[tag + "_chroma"]
+    assert got.shape == want.shape and got.dtype == np.float64
+    err = np.abs(got - want).max()
+    assert err < TOL_F32, err
+    got64 = chroma.wav_samples_to_chroma(audio[tag], compute="fp64")
+    assert np.abs(got64 - want).max() < TOL_F64
+    # unit columns
+    assert np.allclose(np.linalg.norm(got, axis=0), 1.0, atol=1e-5)
+
+
+def test_raw_chroma_unnormalised(chroma, audio):
+    got = chroma.wav_samples_to_chroma(audio["ref"], normalize=False, compute="fp64")
+    want = audio["ref_raw"]
+    assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
+    got32 = chroma.create_chroma(chroma.create_stft(audio["ref"]), normalize=False)
+    assert np.abs(got32 - want).max() <= 1e-4 * np.abs(want).max()
+
+
+def test_single_column(chroma, audio):
+    for k, s in enumerate((0, 2048, 50000, 200000)):
+        col = chroma.wav_to_chroma_col(audio["live"][s : s + 4096])
+        assert col.shape == (12,)
+        assert np.abs(col - audio["live_cols"][k]).max() < TOL_F32
+        col64 = chroma.wav_to_chroma_col(audio["live"][s : s + 4096], compute="fp64")
+        assert np.abs(col64 - audio["live_cols"][k]).max() < TOL_F64
+    with pytest.raises(AssertionError):
+        chroma.wav_to_chroma_col(np.zeros(100))
+
+
+def test_batch_ragged_silence_and_short_tracks(chroma, orc):
+    rng = np.random.default_rng(2)
+    sr = 22050
+    t = np.arange(3 * sr) / sr
+    tone = (0.5 * np.sin(2 * np.pi * 440 * t) + 0.25 * np.sin(2 * np.pi * 660 * t)).astype(np.float32)
+    tracks = [
+        tone,
+        (0.1 * rng.standard_normal(20001)).astype(np.float32),   # odd length
+        np.zeros(10000, dtype=np.float32),                       # silence: zeros stay zeros, no NaN (librosa normalize)
+        np.zeros(100, dtype=np.float32),                         # too short for one frame even with the pad
+        (0.3 * rng.standard_normal(2048)).astype(np.float32),    # exactly one (half-padded) frame
+    ]
+    got = chroma.chroma_batch(tracks)
+    for k, x in enumerate(tracks):
+        want = orc.wav_samples_to_chroma(x)
+        assert got[k].shape == want.shape, k
+        if want.size:
+            assert np.abs(got[k] - want).max() < TOL_F32, k
+            assert np.isfinite(got[k]).all()
+    assert got[2].shape == (12, 3) and not got[2].any()
+    assert got[3].shape == (12, 0)
+    # A4 dominates the tone: chroma class 9 (C-based) is the largest
+    assert int(np.argmax(got[0][:, 10])) == 9
+
+
+def test_chroma_diff(chroma, audio):
+    c = chroma.wav_samples_to_chroma(audio["ref"], compute="fp64")
+    d = chroma.chroma_to_diff(c)
+    assert d.shape == (12, c.shape[1] - 1) and (d >= 0).all()
