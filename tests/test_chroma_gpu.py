@@ -81,7 +81,7 @@ def test_batch_ragged_silence_and_short_tracks(chroma, orc):
         if want.size:
             assert np.abs(got[k] - want).max() < TOL_F32, k
             assert np.isfinite(got[k]).all()
-    assert got[2].shape == (12, 3) and not got[2].any()
+    assert got[2].shape == (12, 4) and not got[2].any()
     assert got[3].shape == (12, 0)
     # A4 dominates the tone: chroma class 9 (C-based) is the largest
     assert int(np.argmax(got[0][:, 10])) == 9
