@@ -141,3 +141,85 @@ class OtwBatch(object):
             n = int(min(lens[s], self.path_cap[s]))
             out.append(flat[self.path_off[s] : self.path_off[s] + n].astype(np.int64))
         return out
+
+
+class WtwBatch(object):
+    """n independent windowed-time-warping aligners fed live chroma columns (kernel K6,
+    csrc/wtw.cu; reference wtw.py:94-128).  W = dtw_win_size/hop_size, h = dtw_hop_size/hop_size."""
+
+    def __init__(self, refs, W, h, device=None):
+        nat.require_cuda()
+        self.device = nat.device() if device is None else torch.device(device)
+        self.W, self.h = int(W), int(h)
+        with torch.cuda.device(self.device):
+            self.d_ref, self.ref_lens, self.ref_offs = _pack_refs(refs, self.device)
+            self.n = int(self.ref_lens.shape[0])
+            L = nat.lib()
+            hd = C.c_void_p()
+            nat.check(L.afs_wtw_create(C.byref(hd), self.n, nat.ptr(self.d_ref), self.ref_lens.ctypes.data_as(nat._i64p),
+                                       self.ref_offs.ctypes.data_as(nat._i64p), 12, self.W, self.h))
+            self._h = hd
+            nbytes = C.c_size_t()
+            nat.check(L.afs_wtw_state_bytes(self._h, C.byref(nbytes)))
+            self.state_bytes = int(nbytes.value)
+            self.state = torch.empty(self.state_bytes, dtype=torch.uint8, device=self.device)
+            self.reset()
+        off, cap = C.c_int64(), C.c_int64()
+        self.path_off = np.empty(self.n, dtype=np.int64)
+        self.path_cap = np.empty(self.n, dtype=np.int64)
+        for s in range(self.n):
+            nat.check(nat.lib().afs_wtw_path_layout(self._h, s, C.byref(off), C.byref(cap)))
+            self.path_off[s], self.path_cap[s] = off.value, cap.value
+        nat.check(nat.lib().afs_wtw_path_layout(self._h, -1, C.byref(off), C.byref(cap)))
+        self.path_total = int(cap.value)
+
+    def reset(self):
+        nat.check(nat.lib().afs_wtw_reset(self._h, nat.ptr(self.state), nat.stream_ptr()))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            nat.lib().afs_wtw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push_device(self, d_cols, active=None):
+        """d_cols: device tensor (n_frames, n, 12) float64.  Returns the device status tensor (n_frames, n)."""
+        if d_cols.dim() == 2:
+            d_cols = d_cols.unsqueeze(0)
+        assert d_cols.is_cuda and d_cols.dtype == torch.float64 and d_cols.is_contiguous()
+        assert d_cols.shape[1] == self.n and d_cols.shape[2] == 12
+        nf = int(d_cols.shape[0])
+        st = torch.empty((nf, self.n), dtype=torch.int32, device=self.device)
+        nat.check(nat.lib().afs_wtw_push(self._h, nat.ptr(d_cols), nf, nat.ptr(active), nat.ptr(st), nat.stream_ptr()))
+        return st
+
+    def push(self, cols):
+        """Host API: cols (n_frames, n, 12) or (n, 12) array -> status array (n_frames, n)."""
+        c = np.ascontiguousarray(cols, dtype=np.float64)
+        if c.ndim == 2:
+            c = c.reshape(1, self.n, 12)
+        return self.push_device(torch.from_numpy(c).to(self.device)).cpu().numpy()
+
+    _dev_view = OtwBatch._dev_view
+
+    def positions(self):
+        """(n, 3) array of (chroma_ptr, live_ptr, ref_ptr)."""
+        p = C.c_void_p()
+        nat.check(nat.lib().afs_wtw_positions_ptr(self._h, C.byref(p)))
+        return self._dev_view(p.value, 3 * self.n, torch.int32).cpu().numpy().reshape(self.n, 3)
+
+    def paths(self):
+        pp, pl = C.c_void_p(), C.c_void_p()
+        nat.check(nat.lib().afs_wtw_path_ptr(self._h, C.byref(pp), C.byref(pl)))
+        lens = self._dev_view(pl.value, self.n, torch.int32).cpu().numpy()
+        flat = self._dev_view(pp.value, 2 * self.path_total, torch.int32).cpu().numpy().reshape(-1, 2)
+        out = []
+        for s in range(self.n):
+            n = int(min(lens[s], self.path_cap[s]))
+            out.append(flat[self.path_off[s] : self.path_off[s] + n].astype(np.int64))
+        return out
