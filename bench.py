@@ -187,6 +187,9 @@ def main():
     ap.add_argument("--pairs", type=int, default=DTW_PAIRS_PER_GPU)
     ap.add_argument("--length", type=int, default=DTW_LEN)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--chroma-tracks", type=int, default=CHROMA_TRACKS)
+    ap.add_argument("--otw-streams", type=int, default=OTW_STREAMS)
+    ap.add_argument("--otw-steps", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -224,10 +227,44 @@ def main():
         return float(t.item())
 
     nat = g.submodule("_native")
-    dtw = g.submodule("dtw")
+    ctx = {"args": args, "rank": rank, "world": world, "local": local, "barrier": barrier, "max_over_ranks": max_over_ranks,
+           "nat": nat, "g": g, "torch": torch}
     wl = ["dtw", "chroma", "otw"] if args.workloads == "all" else args.workloads.split(",")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    results = {}
+    if "dtw" in wl:
+        results["dtw"] = bench_dtw(ctx)
+    if "chroma" in wl:
+        results["chroma"] = bench_chroma(ctx)
+    if "otw" in wl:
+        results["otw"] = bench_otw(ctx)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        head_key = "dtw" if "dtw" in results else list(results)[0]
+        line = dict(results[head_key])
+        for k, v in results.items():
+            if k != head_key:
+                line[k] = v
+        line["clocks"] = clocks
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
 
-    # ---------------- DTW (headline) ----------------
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
+
+
+def bench_dtw(ctx):
+    args, rank, world, torch, nat, g = ctx["args"], ctx["rank"], ctx["world"], ctx["torch"], ctx["nat"], ctx["g"]
+    barrier, max_over_ranks = ctx["barrier"], ctx["max_over_ranks"]
+    dtw = g.submodule("dtw")
     P, Ln = args.pairs, args.length
     live, ref = synth_chroma_pairs(P, Ln, 2000 + rank * P)
     npdt = np.float64 if args.dtype == "fp64" else np.float32
@@ -238,19 +275,12 @@ def main():
     d_b = h_b.to("cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
-    def step_resident():
+    for _ in range(args.warmup_effective):
         plan.accumulate(d_a, d_b)
         plan.backtrack()
-
-    for _ in range(args.warmup_effective):
-        step_resident()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = nat.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
@@ -270,7 +300,7 @@ def main():
     cells_rank = float(plan.cells)
     value = cells_rank * world / (step_ms_max * 1e-3) / 1e9
 
-    # ---------------- e2e: host buffers through the public API objects ----------------
+    # ---- e2e: host (pinned) buffers in, paths out, through the plan object the drop-in API uses ----
     e2e_steps = max(2, min(args.steps, 5))
     h_start = torch.empty(P, dtype=torch.int32).pin_memory()
     h_len = torch.empty(P, dtype=torch.int32).pin_memory()
@@ -298,20 +328,9 @@ def main():
     e2e_val = cells_rank * world / e2e_s / 1e9
     h2d = int(h_a.numel() * h_a.element_size() + h_b.numel() * h_b.element_size())
     d2h = int(h_path.numel() * 4 + h_start.numel() * 4 + h_len.numel() * 4 + h_end.numel() * 8)
-
-    clocks = sampler.stop() if rank == 0 else None
-
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            peaks = json.load(fh)
-    except Exception:
-        pass
+        return None
+    peaks = load_peaks()
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     n_sm = torch.cuda.get_device_properties(0).multi_processor_count
     lanes = FP64_LANES_PER_SM if args.dtype == "fp64" else 128
@@ -319,40 +338,313 @@ def main():
     acc_ms_mean = float(np.mean(acc_ms))
     achieved_tflops = cells_rank * DTW_FLOP_PER_CELL / (acc_ms_mean * 1e-3) / 1e12
     alg_bytes = cells_rank * 0.25 + 2 * P * 12 * Ln * (8 if args.dtype == "fp64" else 4)
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {
         "kernel": "dtw_wavefront_kernel<%s>" % ("double" if args.dtype == "fp64" else "float"),
         "bound": "fp64_pipe" if args.dtype == "fp64" else "fp32_pipe",
         "achieved": achieved_tflops, "peak": pipe_peak_tflops, "unit": "TFLOP/s",
         "frac": achieved_tflops / pipe_peak_tflops,
-        "peak_source": "derived: %d SMs x %d lanes x 2 x %.0f MHz (no %s pipe figure in MEASURED_PEAKS.json)" % (n_sm, lanes, sm_max, args.dtype),
+        "peak_source": "derived: %d SMs x %d lanes x 2 x %.0f MHz (MEASURED_PEAKS.json has no %s pipe figure)" % (n_sm, lanes, sm_max, args.dtype),
         "flop_per_cell": DTW_FLOP_PER_CELL, "kernel_ms": acc_ms_mean,
-        "hbm": {"achieved": alg_bytes / (acc_ms_mean * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
-                "frac": alg_bytes / (acc_ms_mean * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)),
+        "hbm": {"achieved": alg_bytes / (acc_ms_mean * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / (acc_ms_mean * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"},
         "traffic": None,
     }
-    cpu = None
-    if not args.no_cpu_baseline:
-        cpu = cpu_dtw_baseline(seconds=args.cpu_seconds)
-    line = {
+    cpu = None if args.no_cpu_baseline else cpu_dtw_baseline(seconds=args.cpu_seconds)
+    return {
         "metric": "dtw_gcups", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup_effective, "ms_per_step": step_ms_max, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64" if args.dtype == "fp64" else "f32", "data": "synthetic",
         "config": {"workload": "offline full DTW %dx%d chroma frames, %d pairs per GPU (BASELINE cfg[2]: 256 pairs over 8 GPUs)" % (Ln, Ln, P),
                    "pairs_per_gpu": P, "frames": Ln, "features": 12,
                    "l2": "256 MiB flush between timed steps; per-step working set 3.2 GB direction map > 126 MB L2",
-                   "step": "accumulate (K2) + backtrack (K3)", "parallelism": "pairs sharded, no collective"},
+                   "step": "accumulate (K2) + backtrack (K3)", "parallelism": "pairs sharded over ranks, no collective"},
         "kernel_ms": {"accumulate": acc_ms_mean, "backtrack": float(np.mean(bt_ms))},
         "wall_s_timed_region": t_wall,
         "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "clocks": clocks,
     }
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- chroma (cfg[1])
+CHROMA_TRACKS = 1024
+CHROMA_SECONDS = 300.0
+CHROMA_BYTES_PER_FRAME = 2048 * 4 + 12 * 4      # hop samples read once + 12 floats out
+CHROMA_FLOP_PER_FRAME = 1.9e5
+
+
+def synth_audio_tracks(torch, n_tracks, n_samples, seed, device):
+    """SURVEY.md §8(d) cfg2 generator on the device: random note sequence (0.5 s notes, MIDI 36-84,
+    6 harmonics with 1/h amplitude) + 0.01 N(0,1) noise, float32 in [-1, 1]."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    note = 11025
+    n_notes = (n_samples + note - 1) // note
+    out = torch.empty((n_tracks, n_samples), dtype=torch.float32, device=device)
+    ph = torch.arange(note, device=device, dtype=torch.float32) * (2 * np.pi / 22050.0)
+    chunk = 16
+    for t0 in range(0, n_tracks, chunk):
+        t1 = min(n_tracks, t0 + chunk)
+        midi = torch.randint(36, 85, (t1 - t0, n_notes), generator=gen, device=device).to(torch.float32)
+        freq = 440.0 * torch.pow(2.0, (midi - 69.0) / 12.0)
+        phase = freq[:, :, None] * ph[None, None, :]                       # (tracks, notes, note)
+        x = torch.zeros_like(phase)
+        for hmn in range(1, 7):
+            x += torch.sin(hmn * phase) / hmn
+        x = (0.25 * x).reshape(t1 - t0, -1)[:, :n_samples]
+        x += 0.01 * torch.randn(x.shape, generator=gen, device=device)
+        out[t0:t1] = x.clamp_(-1.0, 1.0)
+    return out
+
+
+def cpu_chroma_baseline(seconds=8.0, threads=None):
+    """numpy oracle (chroma.py:44-75 restated with numpy's own rfft) on a 30 s synthetic track per call."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import afs_oracle as orc
+    threads = threads or os.cpu_count() or 1
+    rng = np.random.default_rng(1000)
+    x = (0.2 * np.sin(2 * np.pi * 440.0 * np.arange(30 * 22050) / 22050.0) + 0.01 * rng.standard_normal(30 * 22050)).astype(np.float32)
+    t_end = time.perf_counter() + seconds
+    counts = [0] * threads
+
+    def work(k):
+        while time.perf_counter() < t_end:
+            counts[k] += orc.wav_samples_to_chroma(x).shape[1]
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(work, range(threads)))
+    dt = time.perf_counter() - t0
+    return {"value": sum(counts) / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": "%d frames of 30 s synthetic tracks (numpy rfft oracle) over %d threads in %.1f s" % (sum(counts), threads, dt)}
+
+
+def bench_chroma(ctx):
+    args, rank, world, torch, nat, g = ctx["args"], ctx["rank"], ctx["world"], ctx["torch"], ctx["nat"], ctx["g"]
+    barrier, max_over_ranks = ctx["barrier"], ctx["max_over_ranks"]
+    ch = g.submodule("chroma")
+    T = args.chroma_tracks
+    n = int(CHROMA_SECONDS * 22050)            # 6 615 000 samples
+    plan = ch.default_plan()
+    audio = synth_audio_tracks(torch, T, n, 1000 + rank, "cuda").reshape(-1)
+    offs = np.arange(T + 1, dtype=np.int64) * n
+    out, foffs = plan.run(audio, offs)
+    frames = int(foffs[-1])
+    steps = args.steps
+    for _ in range(args.warmup_effective):
+        plan.run(audio, offs, d_out=out)
+    barrier()
+    launches0 = nat.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for k in range(steps):
+        ev[k][0].record()
+        plan.run(audio, offs, d_out=out)          # input 27 GB per step >> 126 MB L2: no flush needed
+        ev[k][1].record()
+    barrier()
+    launches = nat.launch_count() - launches0
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    ms_max = max_over_ranks(ms)
+    value = frames * world / (ms_max * 1e-3)
+    # ---- e2e: pinned host audio -> H2D in slabs -> K1 -> D2H chroma; 64 distinct host tracks reused for all slots ----
+    slab_tracks = 64
+    h_slab = audio[: slab_tracks * n].cpu().pin_memory()
+    slab_offs = np.arange(slab_tracks + 1, dtype=np.int64) * n
+    d_slabs = [torch.empty(slab_tracks * n, dtype=torch.float32, device="cuda") for _ in range(2)]
+    frames_slab = frames // T * slab_tracks
+    d_outs = [torch.empty(12 * frames_slab, dtype=torch.float32, device="cuda") for _ in range(2)]
+    h_out = torch.empty((T // slab_tracks, 12 * frames_slab), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream()
+
+    def step_e2e():
+        evs = []
+        for i in range(T // slab_tracks):
+            b = i & 1
+            if i >= 2:
+                copy_stream.wait_event(evs[i - 2])      # slab b is free once its previous kernel + D2H are done
+            with torch.cuda.stream(copy_stream):
+                d_slabs[b].copy_(h_slab, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            torch.cuda.current_stream().wait_event(ready)
+            plan.run(d_slabs[b], slab_offs, d_out=d_outs[b])
+            h_out[i].copy_(d_outs[b], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+            evs.append(done)
+        torch.cuda.synchronize()
+
+    e2e = None
+    if T % slab_tracks == 0:
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = 2
+        for _ in range(e2e_steps):
+            step_e2e()
+        barrier()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        e2e = {"value": frames * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(T * n * 4),
+               "d2h_bytes_per_step": int(12 * frames * 4), "steps": e2e_steps,
+               "note": "64 distinct pinned host tracks reused to fill all %d track slots; double-buffered slabs" % T}
+    if rank != 0:
+        return None
+    peaks = load_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    fp32_peak = n_sm * 128 * 2 * sm_max * 1e6 / 1e12
+    gbs = frames * CHROMA_BYTES_PER_FRAME / (ms * 1e-3) / 1e9
+    tfl = frames * CHROMA_FLOP_PER_FRAME / (ms * 1e-3) / 1e12
+    cpu = None if args.no_cpu_baseline else cpu_chroma_baseline(seconds=min(8.0, args.cpu_seconds))
+    return {
+        "metric": "chroma_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps,
+        "warmup": args.warmup_effective, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
+        "data": "synthetic", "vs_baseline": None,
+        "config": {"workload": "batched chroma extraction: %d synthetic 5-min 22.05 kHz tracks per GPU, n_fft=4096, hop=2048 (BASELINE cfg[1])" % T,
+                   "tracks_per_gpu": T, "frames_per_step": frames, "l2": "27 GB of input per step >> 126 MB L2"},
+        "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"kernel": "chroma_kernel<float>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": gbs / hbm_peak, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
+                     "bytes_per_frame": CHROMA_BYTES_PER_FRAME, "traffic": None,
+                     "fp32": {"achieved": tfl, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tfl / fp32_peak,
+                              "flop_per_frame": CHROMA_FLOP_PER_FRAME,
+                              "peak_source": "derived: %d SMs x 128 lanes x 2 x %.0f MHz" % (n_sm, sm_max)}},
+        "cpu_baseline": cpu,
+    }
+
+
+# ----------------------------------------------------------------------------- OTW latency (cfg[3])
+OTW_STREAMS = 4096
+OTW_REF = 3000
+OTW_LIVE = 3300
+OTW_C = 500
+
+
+def synth_streams(torch, n_streams, n_ref, n_live, seed, device):
+    """per-stream AR(1)-smoothed random chroma reference, live = warped copy + noise."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    x = torch.rand((n_streams * 12, 1, n_ref + 63), generator=gen, device=device, dtype=torch.float64)
+    taps = (0.3 * 0.7 ** torch.arange(63, -1, -1, device=device, dtype=torch.float64)).reshape(1, 1, 64)
+    y = torch.nn.functional.conv1d(x, taps).reshape(n_streams, 12, n_ref)
+    ref = y / y.norm(dim=1, keepdim=True)
+    u = torch.linspace(0, 1, n_live, device=device, dtype=torch.float64)
+    idx = torch.round(torch.clamp(u + 0.08 * torch.sin(6 * np.pi * u), 0, 1) * (n_ref - 1)).long()
+    live = ref[:, :, idx] + 0.05 * torch.rand((n_streams, 12, n_live), generator=gen, device=device, dtype=torch.float64)
+    live = live / live.norm(dim=1, keepdim=True)
+    frames = live.permute(2, 0, 1).contiguous()            # (n_live, n_streams, 12)
+    return ref.contiguous(), frames
+
+
+def cpu_otw_baseline(frames_per_thread=400, threads=None):
+    """Oracle C port of OnlineTimeWarping.insert (otw_eran.py:38-85), c = 500, one stream per host thread."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import afs_oracle as orc
+    threads = threads or os.cpu_count() or 1
+    live, ref = synth_chroma_pairs(1, 1200, 3000)
+    live, ref = live[0], ref[0]
+    lat = [[] for _ in range(threads)]
+
+    def work(k):
+        o = orc.OnlineTimeWarping(ref, {"c": OTW_C, "max_run_count": 3})
+        for i in range(min(live.shape[1], 600 + frames_per_thread)):
+            t0 = time.perf_counter()
+            r = o.insert(live[:, i])
+            if i >= 600:
+                lat[k].append(time.perf_counter() - t0)
+            if r == "stop":
+                break
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(work, range(threads)))
+    dt = time.perf_counter() - t0
+    allv = np.array([v for l in lat for v in l]) * 1e3
+    return {"value": float(np.percentile(allv, 99)), "unit": "ms p99 per frame per stream", "p50_ms": float(np.percentile(allv, 50)),
+            "cores": threads, "kind": "port",
+            "streams_per_ms_all_cores": threads / float(np.mean(allv)),
+            "sample": "%d inserts (steady state, c=500) on %d threads, one stream each, %.1f s" % (len(allv), threads, dt)}
+
+
+def bench_otw(ctx):
+    args, rank, world, torch, nat, g = ctx["args"], ctx["rank"], ctx["world"], ctx["torch"], ctx["nat"], ctx["g"]
+    barrier, max_over_ranks = ctx["barrier"], ctx["max_over_ranks"]
+    batch = g.submodule("batch")
+    S = args.otw_streams
+    ref, frames = synth_streams(torch, S, OTW_REF, OTW_LIVE, 3000 + rank, "cuda")
+    res = {}
+    for kind in ("otw", "livenote_v2"):
+        b = batch.OtwBatch(ref, OTW_C, 3, kind=kind)
+        st, npts, pts = b._outputs(1)
+        h_st = torch.empty_like(st, device="cpu").pin_memory()
+        h_np = torch.empty_like(npts, device="cpu").pin_memory()
+        h_pts = torch.empty_like(pts, device="cpu").pin_memory()
+        h_frames = frames.cpu().pin_memory() if kind == "otw" else None
+        warm = OTW_C + 100
+        n_meas = min(2000, OTW_LIVE - warm - 100) if args.otw_steps <= 0 else args.otw_steps
+        lat = []
+        launches0 = nat.launch_count()
+        dev_ms = []
+        for k in range(warm + n_meas):
+            fr = frames[k]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e0.record()
+            b.step_device(fr)
+            e1.record()
+            h_st.copy_(st, non_blocking=True)
+            h_np.copy_(npts, non_blocking=True)
+            h_pts.copy_(pts, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if k >= warm:
+                lat.append(dt * 1e3)
+                dev_ms.append(e0.elapsed_time(e1))
+        launches = nat.launch_count() - launches0
+        # e2e: the frame batch starts in pinned HOST memory (H2D inside the timed region)
+        lat_e2e = []
+        if h_frames is not None:
+            b.reset()
+            d_fr = torch.empty_like(frames[0])
+            for k in range(warm + 500):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                d_fr.copy_(h_frames[k], non_blocking=True)
+                b.step_device(d_fr)
+                h_st.copy_(st, non_blocking=True)
+                h_np.copy_(npts, non_blocking=True)
+                h_pts.copy_(pts, non_blocking=True)
+                torch.cuda.synchronize()
+                if k >= warm:
+                    lat_e2e.append((time.perf_counter() - t0) * 1e3)
+        lat = np.array(lat)
+        p99 = max_over_ranks(float(np.percentile(lat, 99)))
+        p50 = max_over_ranks(float(np.percentile(lat, 50)))
+        res[kind] = {"p99_ms": p99, "p50_ms": p50, "max_ms": float(lat.max()), "steps": int(len(lat)),
+                     "kernel_ms_mean": float(np.mean(dev_ms)), "kernel_ms_p99": float(np.percentile(dev_ms, 99)),
+                     "gpu_launches": int(launches),
+                     "stream_steps_per_s": S * world / (float(np.mean(lat)) * 1e-3)}
+        if lat_e2e:
+            le = np.array(lat_e2e)
+            res[kind]["e2e"] = {"value": max_over_ranks(float(np.percentile(le, 99))), "unit": "ms p99 per frame", "p50_ms": float(np.percentile(le, 50)),
+                                "h2d_bytes_per_step": int(S * 12 * 8), "d2h_bytes_per_step": int(h_st.numel() * 4 + h_np.numel() * 4 + h_pts.numel() * 4),
+                                "steps": int(len(le))}
+        b.close()
+    if rank != 0:
+        return None
+    cpu = None if args.no_cpu_baseline else cpu_otw_baseline()
+    o = res["otw"]
+    return {
+        "metric": "otw_p99_frame_latency_ms", "value": o["p99_ms"], "unit": "ms", "n_gpus": world, "higher_is_better": False,
+        "steps": o["steps"], "warmup": OTW_C + 100, "ms_per_step": o["p50_ms"], "scaling": "weak", "dtype": "f64", "data": "synthetic", "vs_baseline": None,
+        "config": {"workload": "online OTW (otw_eran) streaming alignment, %d concurrent streams per GPU, c=%d, max_run_count=3, ref %d frames (BASELINE cfg[3])" % (S, OTW_C, OTW_REF),
+                   "latency": "host wall time from 'frame batch resident in HBM' to 'status/points of all streams visible on the host', one launch per frame"},
+        "otw": o, "livenote_v2": res["livenote_v2"], "e2e": o.get("e2e"), "gpu_launches": o["gpu_launches"],
+        "cpu_baseline": cpu,
+    }
 
 
 if __name__ == "__main__":
