@@ -89,10 +89,59 @@ struct Lane {
     T bottom;
 };
 
+// ---- async staging of seq_b: 4-slot ring of 32-column chunks per warp ----------------
+// Chunk c holds b[0..11][32c .. 32c+31] as [k][32].  While the warp works on step group
+// s0 (lanes touch chunks s0/32 - 1 and s0/32) chunk s0/32 + 2 is in flight.  Aligned
+// shapes use TMA bulk copies (cp.async.bulk -> mbarrier complete_tx); anything else
+// falls back to per-lane cp.async (LDGSTS), which has no alignment requirement.
+constexpr int kChunkCols = 32;
+constexpr int kRingSlots = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+template <int BYTES> __device__ __forceinline__ void cp_async_elem(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst)), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T>
+struct WarpSmem {
+    T ring[kRingSlots][kF][kChunkCols];
+    T ubuf[32];
+    T obuf[32];
+    uint64_t mbar[kRingSlots];
+};
+
 template <typename T, bool DENSE, int U>
 __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane, const int band, const DtwPair &pm,
-                                         const T *__restrict__ bp, const T *ubuf, T *obuf, const bool feeds_next,
-                                         uint32_t &dw, const DtwArgs<T> &args, const int pair)
+                                         WarpSmem<T> &sm, const bool feeds_next, uint32_t &dw, const DtwArgs<T> &args,
+                                         const int pair)
 {
     using A = Arith<T>;
     const unsigned full = 0xffffffffu;
@@ -100,17 +149,18 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
     const int j = s - lane;
     // inputs for the lane's first row: value under the previous lane's last row, one step ago
     T upn = __shfl_up_sync(full, L.bottom, 1);
-    T ub = ubuf[s & 31];
+    T ub = sm.ubuf[s & 31];
     T up = (lane == 0) ? ub : upn;
     if ((unsigned)j < (unsigned)N) {
         T c[kRows];
         {
-            T bk = __ldg(bp + j);
+            const T *bs = &sm.ring[(j >> 5) & (kRingSlots - 1)][0][j & (kChunkCols - 1)];
+            T bk = bs[0];
 #pragma unroll
             for (int r = 0; r < kRows; r++) c[r] = A::mul(L.ar[r][0], bk);
 #pragma unroll
             for (int k = 1; k < kF; k++) {
-                bk = __ldg(bp + (int64_t)k * N + j);
+                bk = bs[k * kChunkCols];
 #pragma unroll
                 for (int r = 0; r < kRows; r++) c[r] = A::fma(L.ar[r][k], bk, c[r]);
             }
@@ -147,7 +197,7 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
         L.up_prev = up;
         L.bottom = L.left[kRows - 1];
         dw |= nib << (8 * U);
-        if (feeds_next && lane == 31) obuf[s & 31] = L.bottom;
+        if (feeds_next && lane == 31) sm.obuf[s & 31] = L.bottom;
         if (j == N - 1) {
             const int rl = pm.M - 1 - (band * kBandRows + lane * kRows);   // row of (M-1) inside this lane
             if (rl >= 0 && rl < kRows) {
@@ -164,13 +214,20 @@ template <typename T, bool DENSE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(const DtwArgs<T> args)
 {
     using A = Arith<T>;
-    __shared__ T s_ubuf[kWarpsPerBlock][32];
-    __shared__ T s_obuf[kWarpsPerBlock][32];
+    extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
-    T *ubuf = s_ubuf[w];
-    T *obuf = s_obuf[w];
+    WarpSmem<T> &sm = reinterpret_cast<WarpSmem<T> *>(s_dyn)[w];
     const unsigned full = 0xffffffffu;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < kRingSlots; q++) mbar_init(&sm.mbar[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t phase_bits = 0;      // bit q: mbarrier phase parity of ring slot q's next completed fill
 
     for (;;) {
         int q = 0;
@@ -189,6 +246,35 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
         int *prog_cur = args.prog + pm.prog_off + band;
         const int *prog_prev = prog_cur - 1;
         uint4 *dirp = args.dir + pm.dir_off + (int64_t)band * 32 + lane;
+        const int nchunks = (N + kChunkCols - 1) / kChunkCols;
+        // TMA bulk copies need 16-byte aligned rows: every row start (b + k*N + 32c) and every length
+        const bool bulk = ((reinterpret_cast<uintptr_t>(bp) & 15) == 0) && ((N * (int)sizeof(T)) % 16 == 0);
+
+        // stage chunk c of seq_b into ring slot (c & 3)
+        auto stage = [&](int c) {
+            if (bulk) {
+                if (c < nchunks && lane == 0) {
+                    const int cols = min(kChunkCols, N - c * kChunkCols);
+                    const uint32_t bytes = (uint32_t)(cols * sizeof(T));
+                    uint64_t *bar = &sm.mbar[c & (kRingSlots - 1)];
+                    mbar_expect_tx(bar, bytes * kF);
+#pragma unroll
+                    for (int k = 0; k < kF; k++)
+                        bulk_g2s(&sm.ring[c & (kRingSlots - 1)][k][0], bp + (int64_t)k * N + c * kChunkCols, bytes, bar);
+                }
+            } else {
+                const int col = c * kChunkCols + lane;
+                if (c < nchunks && col < N) {
+#pragma unroll
+                    for (int k = 0; k < kF; k++)
+                        cp_async_elem<sizeof(T)>(&sm.ring[c & (kRingSlots - 1)][k][lane], bp + (int64_t)k * N + col);
+                }
+                cp_async_commit();      // always commit: group count stays in lock-step with the chunk index
+            }
+        };
+        __syncwarp();          // previous band's readers are done with every slot
+        stage(0);
+        stage(1);
 
         Lane<T> L;
         {
@@ -203,12 +289,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
             L.up_prev = A::inf();
             L.bottom = A::inf();
         }
-        __syncwarp();
-        ubuf[lane] = A::inf();          // band 0: nothing above the first row
+        sm.ubuf[lane] = A::inf();          // band 0: nothing above the first row
         __syncwarp();
 
         uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
         for (int s0 = 0; s0 < pm.nsteps; s0 += 32) {
+            const int c0 = s0 >> 5;
+            // ---- chunk c0 of seq_b must have landed; then put chunk c0+2 in flight ----
+            if (bulk) {
+                if (c0 < nchunks) {
+                    const int slot = c0 & (kRingSlots - 1);
+                    mbar_wait(&sm.mbar[slot], (phase_bits >> slot) & 1u);
+                    phase_bits ^= 1u << slot;      // every fill of a slot is waited for exactly once, in order
+                }
+            } else {
+                cp_async_wait<1>();
+            }
+            __syncwarp();
+            stage(c0 + 2);
             if (band > 0 && s0 < N) {
                 // wait until the band above has published columns [s0, s0+32)
                 const int need = min(s0 + 32, N);
@@ -216,17 +314,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
                 const int col = s0 + lane;
                 T v = (col < N) ? __ldcg(brow_prev + col) : A::inf();
                 __syncwarp();
-                ubuf[lane] = v;
+                sm.ubuf[lane] = v;
                 __syncwarp();
             }
 #pragma unroll 1
             for (int g4 = 0; g4 < 8; g4++) {
                 const int s = s0 + g4 * 4;
                 uint32_t dw = 0;
-                dtw_step<T, DENSE, 0>(L, s + 0, lane, band, pm, bp, ubuf, obuf, feeds_next, dw, args, it.pair);
-                dtw_step<T, DENSE, 1>(L, s + 1, lane, band, pm, bp, ubuf, obuf, feeds_next, dw, args, it.pair);
-                dtw_step<T, DENSE, 2>(L, s + 2, lane, band, pm, bp, ubuf, obuf, feeds_next, dw, args, it.pair);
-                dtw_step<T, DENSE, 3>(L, s + 3, lane, band, pm, bp, ubuf, obuf, feeds_next, dw, args, it.pair);
+                dtw_step<T, DENSE, 0>(L, s + 0, lane, band, pm, sm, feeds_next, dw, args, it.pair);
+                dtw_step<T, DENSE, 1>(L, s + 1, lane, band, pm, sm, feeds_next, dw, args, it.pair);
+                dtw_step<T, DENSE, 2>(L, s + 2, lane, band, pm, sm, feeds_next, dw, args, it.pair);
+                dtw_step<T, DENSE, 3>(L, s + 3, lane, band, pm, sm, feeds_next, dw, args, it.pair);
                 d0 = d1; d1 = d2; d2 = d3; d3 = dw;
                 if ((g4 & 3) == 3) {
                     const int cbp = s >> 4;
@@ -237,12 +335,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
                 // slots 0..31 hold lane 31's columns s0-31 .. s0
                 __syncwarp();
                 const int col = s0 - 31 + lane;
-                if (col >= 0 && col < N) __stcg(brow_cur + col, obuf[lane]);
+                if (col >= 0 && col < N) __stcg(brow_cur + col, sm.obuf[lane]);
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) afs::st_release(prog_cur, min(s0 + 1, N));
             }
         }
+        if (!bulk) cp_async_wait<0>();
     }
 }
 
@@ -405,13 +504,15 @@ static int launch_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b,
     AFS_CUDA(cudaMemsetAsync(args.prog, 0, pl->prog_bytes, st));
     const bool dense = dense_cost != nullptr;
     auto kern = dense ? dtw_wavefront_kernel<T, true> : dtw_wavefront_kernel<T, false>;
+    const size_t smem = sizeof(WarpSmem<T>) * kWarpsPerBlock;
+    AFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    AFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerBlock * 32, 0));
+    AFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerBlock * 32, smem));
     if (occ < 1) return afs::fail(AFS_ERR_CUDA, "dtw kernel does not fit on an SM");
     int blocks = afs::sm_count() * occ;
     const int need = (args.n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > need) blocks = need;
-    kern<<<blocks, kWarpsPerBlock * 32, 0, st>>>(args);
+    kern<<<blocks, kWarpsPerBlock * 32, smem, st>>>(args);
     afs::count_launch();
     AFS_CUDA(cudaGetLastError());
     return AFS_OK;
