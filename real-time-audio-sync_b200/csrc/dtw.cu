@@ -11,6 +11,10 @@
 //   step s : lane l processes column j = s - l  (anti-diagonal skew inside the warp);
 //            the value under the lane's last row travels to lane l+1 by warp shuffle
 //            (the `up`/`diag` inputs of the next lane's first row);
+//   seq_b  : re-packed once per call to column-major [N][12 (+2 pad)] so that a chunk of
+//            32 columns is ONE contiguous TMA bulk copy (cp.async.bulk -> mbarrier) into a
+//            4-slot shared-memory ring per warp, and a lane fetches its column with
+//            128-bit shared loads at a compile-time stride (bank-conflict free);
 //   band b needs the last row of band b-1: it is streamed through an L2-resident
 //   ring of two rows per pair in chunks of 32 columns, guarded by a release/acquire
 //   progress counter per band.  Bands are claimed from one global atomic ticket in
@@ -34,18 +38,26 @@ constexpr int kF = 12;           // chroma features (F = 12 every
 constexpr int kRows = 4;         // rows per lane
 constexpr int kBandRows = 32 * kRows;
 constexpr int kWarpsPerBlock = 4;
+constexpr int kChunkCols = 32;   // columns per staged chunk of seq_b
+constexpr int kRingSlots = 4;    // chunks resident per warp
+
+// packed seq_b: elements per column.  fp64: 12 + 2 pad = 112 B (lane stride 28 words: the 8
+// lanes of a 128-bit shared-load phase hit 8 distinct 4-word bank groups); fp32: 12 = 48 B
+// (stride 12 words: also conflict free).
+template <typename T> struct ColStride { static constexpr int value = sizeof(T) == 8 ? 14 : 12; };
 
 struct DtwPair {
     int64_t a_off, b_off;   // element offsets of (12,M) / (12,N)
     int64_t dir_off;        // uint4 units into the direction area
     int64_t brow_off;       // elements into the hand-off area (2 rows of nsteps)
+    int64_t bt_off;         // elements into the packed seq_b area
     int64_t path_off;       // pairs into the path area
     int32_t M, N;
     int32_t nbands, gpad;   // gpad = nbands * 32 row groups
     int32_t nsteps;         // roundup32(N + 31)
     int32_t prog_off;       // first progress counter of this pair
     int32_t path_cap;       // M + N
-    int32_t pad_;
+    int32_t nchunks;        // ceil(N / 32)
 };
 
 struct DtwItem { int32_t pair, band; };
@@ -57,6 +69,15 @@ template <> struct Arith<double> {
     static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ void load_col(const double *p, double (&bk)[kF])
+    {
+#pragma unroll
+        for (int q = 0; q < kF / 2; q++) {
+            const double2 v = reinterpret_cast<const double2 *>(p)[q];
+            bk[2 * q] = v.x;
+            bk[2 * q + 1] = v.y;
+        }
+    }
 };
 template <> struct Arith<float> {
     static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
@@ -64,6 +85,17 @@ template <> struct Arith<float> {
     static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ void load_col(const float *p, float (&bk)[kF])
+    {
+#pragma unroll
+        for (int q = 0; q < kF / 4; q++) {
+            const float4 v = reinterpret_cast<const float4 *>(p)[q];
+            bk[4 * q] = v.x;
+            bk[4 * q + 1] = v.y;
+            bk[4 * q + 2] = v.z;
+            bk[4 * q + 3] = v.w;
+        }
+    }
 };
 
 template <typename T>
@@ -74,6 +106,7 @@ struct DtwArgs {
     int n_items;
     uint4 *dir;
     T *brow;
+    T *bt;
     int *prog;
     int *ticket;
     double *acc_end;
@@ -89,14 +122,6 @@ struct Lane {
     T bottom;
 };
 
-// ---- async staging of seq_b: 4-slot ring of 32-column chunks per warp ----------------
-// Chunk c holds b[0..11][32c .. 32c+31] as [k][32].  While the warp works on step group
-// s0 (lanes touch chunks s0/32 - 1 and s0/32) chunk s0/32 + 2 is in flight.  Aligned
-// shapes use TMA bulk copies (cp.async.bulk -> mbarrier complete_tx); anything else
-// falls back to per-lane cp.async (LDGSTS), which has no alignment requirement.
-constexpr int kChunkCols = 32;
-constexpr int kRingSlots = 4;
-
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
@@ -107,6 +132,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -123,51 +149,57 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
                      : "memory");
     } while (!done);
 }
-template <int BYTES> __device__ __forceinline__ void cp_async_elem(void *dst, const void *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst)), "l"(src), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <typename T>
 struct WarpSmem {
-    T ring[kRingSlots][kF][kChunkCols];
+    T ring[kRingSlots * kChunkCols * ColStride<T>::value];   // column (j & 127) at ring + (j & 127) * stride
     T ubuf[32];
     T obuf[32];
     uint64_t mbar[kRingSlots];
 };
 
+// seq_b (12, N) feature-major -> [N_pad][stride] column-major (+ zero padding)
+template <typename T>
+__global__ void dtw_pack_b_kernel(const T *__restrict__ b, T *__restrict__ bt, const DtwPair *pairs, int n_pairs)
+{
+    constexpr int S = ColStride<T>::value;
+    const int p = blockIdx.y;
+    const DtwPair pm = pairs[p];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= pm.nchunks * kChunkCols) return;
+    const T *src = b + pm.b_off;
+    T *dst = bt + pm.bt_off + (int64_t)j * S;
+#pragma unroll
+    for (int k = 0; k < S; k++) dst[k] = (k < kF && j < pm.N) ? __ldg(src + (int64_t)k * pm.N + j) : (T)0;
+}
+
 template <typename T, bool DENSE, int U>
 __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane, const int band, const DtwPair &pm,
-                                         WarpSmem<T> &sm, const bool feeds_next, uint32_t &dw, const DtwArgs<T> &args,
-                                         const int pair)
+                                         WarpSmem<T> &sm, const bool feeds_next, uint32_t &dw, const DtwArgs<T> &args)
 {
     using A = Arith<T>;
+    constexpr int S = ColStride<T>::value;
     const unsigned full = 0xffffffffu;
     const int N = pm.N;
     const int j = s - lane;
-    // inputs for the lane's first row: value under the previous lane's last row, one step ago
-    T upn = __shfl_up_sync(full, L.bottom, 1);
-    T ub = sm.ubuf[s & 31];
-    T up = (lane == 0) ? ub : upn;
+    // inputs for the lane's first row: value under the previous lane's last row, one step ago;
+    // lane 0 takes it from the band above (staged in ubuf)
+    T up = __shfl_up_sync(full, L.bottom, 1);
+    if (lane == 0) up = sm.ubuf[s & 31];
     if ((unsigned)j < (unsigned)N) {
         T c[kRows];
         {
-            const T *bs = &sm.ring[(j >> 5) & (kRingSlots - 1)][0][j & (kChunkCols - 1)];
-            T bk = bs[0];
+            T bk[kF];
+            A::load_col(sm.ring + (j & (kRingSlots * kChunkCols - 1)) * S, bk);
 #pragma unroll
-            for (int r = 0; r < kRows; r++) c[r] = A::mul(L.ar[r][0], bk);
+            for (int r = 0; r < kRows; r++) c[r] = A::mul(L.ar[r][0], bk[0]);
 #pragma unroll
-            for (int k = 1; k < kF; k++) {
-                bk = bs[k * kChunkCols];
+            for (int k = 1; k < kF; k++)
 #pragma unroll
-                for (int r = 0; r < kRows; r++) c[r] = A::fma(L.ar[r][k], bk, c[r]);
-            }
+                for (int r = 0; r < kRows; r++) c[r] = A::fma(L.ar[r][k], bk[k], c[r]);
 #pragma unroll
             for (int r = 0; r < kRows; r++) c[r] = A::sub((T)1, c[r]);    // dtw.py:11
         }
-        const bool origin = (band == 0) && (s == 0) && (lane == 0);      // dtw.py:20-21
         T diag = L.up_prev;
         T upv = up;
         uint32_t nib = 0;
@@ -176,7 +208,6 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
             T x = A::add(L.left[r], c[r]);                  // (i, j-1)   dtw.py:35
             T y = A::add(upv, c[r]);                        // (i-1, j)   dtw.py:36
             T z = A::fma((T)2, c[r], diag);                 // (i-1, j-1) dtw.py:37 (2c exact)
-            if (r == 0 && origin) z = c[r];
             const bool yx = y < x;                          // np.argmin: first minimum wins
             T m = yx ? y : x;
             const bool zm = z < m;
@@ -198,15 +229,6 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
         L.bottom = L.left[kRows - 1];
         dw |= nib << (8 * U);
         if (feeds_next && lane == 31) sm.obuf[s & 31] = L.bottom;
-        if (j == N - 1) {
-            const int rl = pm.M - 1 - (band * kBandRows + lane * kRows);   // row of (M-1) inside this lane
-            if (rl >= 0 && rl < kRows) {
-                T e = L.left[0];
-#pragma unroll
-                for (int r = 1; r < kRows; r++) if (rl == r) e = L.left[r];
-                args.acc_end[pair] = (double)e;
-            }
-        }
     }
 }
 
@@ -214,6 +236,8 @@ template <typename T, bool DENSE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(const DtwArgs<T> args)
 {
     using A = Arith<T>;
+    constexpr int S = ColStride<T>::value;
+    constexpr uint32_t kChunkBytes = kChunkCols * S * sizeof(T);
     extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
@@ -240,36 +264,20 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
         const int N = pm.N;
         const bool feeds_next = band + 1 < pm.nbands;
         const T *ap = args.a + pm.a_off;
-        const T *bp = args.b + pm.b_off;
+        const T *btp = args.bt + pm.bt_off;
         T *brow_cur = args.brow + pm.brow_off + (int64_t)(band & 1) * pm.nsteps;
         const T *brow_prev = args.brow + pm.brow_off + (int64_t)((band + 1) & 1) * pm.nsteps;
         int *prog_cur = args.prog + pm.prog_off + band;
         const int *prog_prev = prog_cur - 1;
         uint4 *dirp = args.dir + pm.dir_off + (int64_t)band * 32 + lane;
-        const int nchunks = (N + kChunkCols - 1) / kChunkCols;
-        // TMA bulk copies need 16-byte aligned rows: every row start (b + k*N + 32c) and every length
-        const bool bulk = ((reinterpret_cast<uintptr_t>(bp) & 15) == 0) && ((N * (int)sizeof(T)) % 16 == 0);
+        const int nchunks = pm.nchunks;
 
-        // stage chunk c of seq_b into ring slot (c & 3)
+        // stage chunk c of packed seq_b into ring slot (c & 3): one TMA bulk copy
         auto stage = [&](int c) {
-            if (bulk) {
-                if (c < nchunks && lane == 0) {
-                    const int cols = min(kChunkCols, N - c * kChunkCols);
-                    const uint32_t bytes = (uint32_t)(cols * sizeof(T));
-                    uint64_t *bar = &sm.mbar[c & (kRingSlots - 1)];
-                    mbar_expect_tx(bar, bytes * kF);
-#pragma unroll
-                    for (int k = 0; k < kF; k++)
-                        bulk_g2s(&sm.ring[c & (kRingSlots - 1)][k][0], bp + (int64_t)k * N + c * kChunkCols, bytes, bar);
-                }
-            } else {
-                const int col = c * kChunkCols + lane;
-                if (c < nchunks && col < N) {
-#pragma unroll
-                    for (int k = 0; k < kF; k++)
-                        cp_async_elem<sizeof(T)>(&sm.ring[c & (kRingSlots - 1)][k][lane], bp + (int64_t)k * N + col);
-                }
-                cp_async_commit();      // always commit: group count stays in lock-step with the chunk index
+            if (c < nchunks && lane == 0) {
+                uint64_t *bar = &sm.mbar[c & (kRingSlots - 1)];
+                mbar_expect_tx(bar, kChunkBytes);
+                bulk_g2s(sm.ring + (c & (kRingSlots - 1)) * (kChunkCols * S), btp + (int64_t)c * (kChunkCols * S), kChunkBytes, bar);
             }
         };
         __syncwarp();          // previous band's readers are done with every slot
@@ -288,6 +296,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
             for (int r = 0; r < kRows; r++) L.left[r] = A::inf();
             L.up_prev = A::inf();
             L.bottom = A::inf();
+            // dtw.py:20-21: acc[0,0] = cost[0,0], back = 2.  A virtual diagonal neighbour of
+            // -cost[0,0] makes (0,0) an ordinary cell: fma(2, c, -c) == c exactly, code 2; the
+            // slot (up_prev) is overwritten right after, so nothing else ever sees it.
+            if (band == 0 && lane == 0) {
+                T s = A::mul(L.ar[0][0], __ldg(btp));
+#pragma unroll
+                for (int k = 1; k < kF; k++) s = A::fma(L.ar[0][k], __ldg(btp + k), s);
+                L.up_prev = -A::sub((T)1, s);
+            }
         }
         sm.ubuf[lane] = A::inf();          // band 0: nothing above the first row
         __syncwarp();
@@ -296,16 +313,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
         for (int s0 = 0; s0 < pm.nsteps; s0 += 32) {
             const int c0 = s0 >> 5;
             // ---- chunk c0 of seq_b must have landed; then put chunk c0+2 in flight ----
-            if (bulk) {
-                if (c0 < nchunks) {
-                    const int slot = c0 & (kRingSlots - 1);
-                    mbar_wait(&sm.mbar[slot], (phase_bits >> slot) & 1u);
-                    phase_bits ^= 1u << slot;      // every fill of a slot is waited for exactly once, in order
-                }
-            } else {
-                cp_async_wait<1>();
+            if (c0 < nchunks) {
+                const int slot = c0 & (kRingSlots - 1);
+                mbar_wait(&sm.mbar[slot], (phase_bits >> slot) & 1u);
+                phase_bits ^= 1u << slot;      // every fill of a slot is waited for exactly once, in order
             }
-            __syncwarp();
+            __syncwarp();                      // all lanes are done with chunk c0-2 (same slot as c0+2)
             stage(c0 + 2);
             if (band > 0 && s0 < N) {
                 // wait until the band above has published columns [s0, s0+32)
@@ -321,10 +334,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
             for (int g4 = 0; g4 < 8; g4++) {
                 const int s = s0 + g4 * 4;
                 uint32_t dw = 0;
-                dtw_step<T, DENSE, 0>(L, s + 0, lane, band, pm, sm, feeds_next, dw, args, it.pair);
-                dtw_step<T, DENSE, 1>(L, s + 1, lane, band, pm, sm, feeds_next, dw, args, it.pair);
-                dtw_step<T, DENSE, 2>(L, s + 2, lane, band, pm, sm, feeds_next, dw, args, it.pair);
-                dtw_step<T, DENSE, 3>(L, s + 3, lane, band, pm, sm, feeds_next, dw, args, it.pair);
+                dtw_step<T, DENSE, 0>(L, s + 0, lane, band, pm, sm, feeds_next, dw, args);
+                dtw_step<T, DENSE, 1>(L, s + 1, lane, band, pm, sm, feeds_next, dw, args);
+                dtw_step<T, DENSE, 2>(L, s + 2, lane, band, pm, sm, feeds_next, dw, args);
+                dtw_step<T, DENSE, 3>(L, s + 3, lane, band, pm, sm, feeds_next, dw, args);
                 d0 = d1; d1 = d2; d2 = d3; d3 = dw;
                 if ((g4 & 3) == 3) {
                     const int cbp = s >> 4;
@@ -341,7 +354,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
                 if (lane == 0) afs::st_release(prog_cur, min(s0 + 1, N));
             }
         }
-        if (!bulk) cp_async_wait<0>();
+        // after the sweep every lane's left[] holds column N-1: acc_cost[M-1, N-1] sits in one of them
+        {
+            const int rl = pm.M - 1 - (band * kBandRows + lane * kRows);
+            if (rl >= 0 && rl < kRows) {
+                T e = L.left[0];
+#pragma unroll
+                for (int r = 1; r < kRows; r++) if (rl == r) e = L.left[r];
+                args.acc_end[it.pair] = (double)e;
+            }
+        }
     }
 }
 
@@ -383,9 +405,10 @@ struct afs_dtw_plan {
     std::vector<DtwItem> items;
     DtwPair *d_pairs = nullptr;
     DtwItem *d_items = nullptr;
-    size_t dir_bytes = 0, brow_bytes = 0, prog_bytes = 0;
+    size_t dir_bytes = 0, brow_bytes = 0, bt_bytes = 0, prog_bytes = 0;
     int64_t total_path = 0;
     int total_bands = 0;
+    int max_cols_pad = 0;
 };
 
 extern "C" {
@@ -401,7 +424,9 @@ int afs_dtw_plan_create(afs_dtw_plan **out, int n_pairs, const int64_t *h_len_a,
     pl->n_pairs = n_pairs;
     pl->dtype = dtype;
     pl->pairs.resize(n_pairs);
-    int64_t dir_units = 0, brow_elems = 0, path_pairs = 0;
+    const int stride = dtype == AFS_F64 ? ColStride<double>::value : ColStride<float>::value;
+    const size_t esz = dtype == AFS_F64 ? 8 : 4;
+    int64_t dir_units = 0, brow_elems = 0, bt_elems = 0, path_pairs = 0;
     int prog = 0, max_bands = 0;
     for (int p = 0; p < n_pairs; p++) {
         const int64_t M = h_len_a[p], N = h_len_b[p];
@@ -417,17 +442,20 @@ int afs_dtw_plan_create(afs_dtw_plan **out, int n_pairs, const int64_t *h_len_a,
         q.nbands = (int32_t)((M + kBandRows - 1) / kBandRows);
         q.gpad = q.nbands * 32;
         q.nsteps = (int32_t)((N + 31 + 31) / 32 * 32);
+        q.nchunks = (int32_t)((N + kChunkCols - 1) / kChunkCols);
         q.dir_off = dir_units;
         q.brow_off = brow_elems;
+        q.bt_off = bt_elems;
         q.path_off = path_pairs;
         q.prog_off = prog;
         q.path_cap = (int32_t)(M + N);
-        q.pad_ = 0;
         dir_units += (int64_t)(q.nsteps / 16) * q.gpad;
         brow_elems += 2 * (int64_t)q.nsteps;
+        bt_elems += (int64_t)q.nchunks * kChunkCols * stride;     // whole chunks: every bulk copy is full and 16 B aligned
         path_pairs += q.path_cap;
         prog += q.nbands;
         if (q.nbands > max_bands) max_bands = q.nbands;
+        if (q.nchunks * kChunkCols > pl->max_cols_pad) pl->max_cols_pad = q.nchunks * kChunkCols;
     }
     // ticket order: band-major, pairs interleaved -> every dependency has a smaller ticket
     for (int b = 0; b < max_bands; b++)
@@ -436,7 +464,8 @@ int afs_dtw_plan_create(afs_dtw_plan **out, int n_pairs, const int64_t *h_len_a,
     pl->total_bands = prog;
     pl->total_path = path_pairs;
     pl->dir_bytes = afs::align_up((size_t)dir_units * 16, 256);
-    pl->brow_bytes = afs::align_up((size_t)brow_elems * (dtype == AFS_F64 ? 8 : 4), 256);
+    pl->brow_bytes = afs::align_up((size_t)brow_elems * esz, 256);
+    pl->bt_bytes = afs::align_up((size_t)bt_elems * esz, 256);
     pl->prog_bytes = afs::align_up((size_t)(prog + 1) * sizeof(int), 256);
     cudaError_t e = cudaMalloc(&pl->d_pairs, sizeof(DtwPair) * n_pairs);
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_items, sizeof(DtwItem) * pl->items.size());
@@ -464,7 +493,7 @@ int afs_dtw_plan_destroy(afs_dtw_plan *pl)
 int afs_dtw_plan_workspace_bytes(const afs_dtw_plan *pl, size_t *bytes)
 {
     if (!pl || !bytes) return afs::fail(AFS_ERR_INVALID, "afs_dtw_plan_workspace_bytes: null argument");
-    *bytes = pl->dir_bytes + pl->brow_bytes + pl->prog_bytes;
+    *bytes = pl->dir_bytes + pl->brow_bytes + pl->bt_bytes + pl->prog_bytes;
     return AFS_OK;
 }
 
@@ -496,12 +525,20 @@ static int launch_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b,
     args.n_items = (int)pl->items.size();
     args.dir = reinterpret_cast<uint4 *>(base);
     args.brow = reinterpret_cast<T *>(base + pl->dir_bytes);
-    args.prog = reinterpret_cast<int *>(base + pl->dir_bytes + pl->brow_bytes);
+    args.bt = reinterpret_cast<T *>(base + pl->dir_bytes + pl->brow_bytes);
+    args.prog = reinterpret_cast<int *>(base + pl->dir_bytes + pl->brow_bytes + pl->bt_bytes);
     args.ticket = args.prog + pl->total_bands;
     args.acc_end = d_acc_end;
     args.dense_cost = static_cast<T *>(dense_cost);
     args.dense_acc = static_cast<T *>(dense_acc);
     AFS_CUDA(cudaMemsetAsync(args.prog, 0, pl->prog_bytes, st));
+    {
+        const int threads = 128;
+        dim3 grid((pl->max_cols_pad + threads - 1) / threads, pl->n_pairs);
+        dtw_pack_b_kernel<T><<<grid, threads, 0, st>>>(args.b, args.bt, pl->d_pairs, pl->n_pairs);
+        afs::count_launch();
+        AFS_CUDA(cudaGetLastError());
+    }
     const bool dense = dense_cost != nullptr;
     auto kern = dense ? dtw_wavefront_kernel<T, true> : dtw_wavefront_kernel<T, false>;
     const size_t smem = sizeof(WarpSmem<T>) * kWarpsPerBlock;
