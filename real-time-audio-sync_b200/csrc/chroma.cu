@@ -15,6 +15,7 @@
 #include <math_constants.h>
 
 #include <cfloat>
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -257,6 +258,213 @@ __global__ void __launch_bounds__(kThreads) chroma_kernel(const ChromaTables<T> 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fast float32 variant (the throughput path).  Same transform as chroma_kernel<float>, but
+//   * the thread's 32 window values, its 15 pass-1 twiddles and its untangle twiddle base live
+//     in registers for the whole persistent loop; the 128 pass-2 twiddles sit in shared memory;
+//   * the 12 x 2049 filterbank is applied as class-sorted sparse windows: for every bin above the
+//     lowest few, only 6 cyclically adjacent chroma classes carry weight (the rest are < 1e-7 of
+//     the column maximum: Gaussian of 1 semitone width, librosa.filters.chroma).  Bins are sorted
+//     by the first class c0 of their window and dealt to threads so that all bins of a thread share
+//     c0: the thread accumulates 6 statically indexed sums from a [slot][6][thread] weight table
+//     (coalesced, L1 resident) and power values gathered from shared memory.  The handful of
+//     wide low-frequency bins keep all 12 weights ("dense list").
+// The plan builder verifies the structure on the actual matrix and falls back to the generic
+// kernel if it does not hold.
+constexpr int kWin = 6;
+constexpr int kMaxBpt = 24;
+constexpr int kMaxDense = 32;
+constexpr int kZeroSlot = kBins;      // sP[2049] == 0 for unused (thread, slot) entries
+
+struct ChromaFastTables {
+    const float *hann;          // 4096
+    const float2 *tw2048;       // exp(-2 pi i j / 2048)
+    const float2 *tw4096;       // exp(-2 pi i k / 4096), k <= 1024
+    const float *wsp;           // [bpt][6][128]
+    const uint16_t *paddr;      // [bpt][128]
+    const int *cls_start;       // [13] threads [cls_start[c], cls_start[c+1]) have window start c
+    const float *wdense;        // [nd][12]
+    const uint16_t *kdense;     // [nd]
+    int bpt, nd;
+};
+
+__device__ __forceinline__ float2 ld_stream_f2(const float *p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFastTables tb, const ChromaBatch bt)
+{
+    using C = Cx<float>;
+    __shared__ __align__(16) C sA[16 * kStrideA];          // pass-1 output; later Z in natural order; later reduction scratch
+    __shared__ __align__(16) C sB[16 * kStrideB];          // pass-2 output; later the power spectrum (float[2052])
+    __shared__ C sTw2[16 * 8];                              // W_128^(m2 k2) at [k2][m2]
+    __shared__ int sCls[13];
+    const int t = threadIdx.x;
+    const int lane = t & 31;
+
+    // ---- per-thread constants, loaded once ----
+    float win[32];
+    C tw1[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        win[2 * n1] = tb.hann[256 * n1 + 2 * t];
+        win[2 * n1 + 1] = tb.hann[256 * n1 + 2 * t + 1];
+    }
+#pragma unroll
+    for (int k1 = 1; k1 < 16; k1++) { const float2 w = tb.tw2048[t * k1]; tw1[k1] = C{w.x, w.y}; }
+    const float2 twu0 = tb.tw4096[t];                       // W_4096^t ; W_4096^(t + 128 i) = twu0 * W_32^i
+    { const float2 w = tb.tw2048[16 * (t & 7) * (t >> 3)]; sTw2[t] = C{w.x, w.y}; }
+    if (t < 13) sCls[t] = tb.cls_start[t];
+    float *sP = reinterpret_cast<float *>(sB);
+    float *sRed = reinterpret_cast<float *>(sA);            // [6][128] + dense[12] + part[72]
+    __syncthreads();
+
+    for (int64_t f = blockIdx.x; f < bt.total_frames; f += gridDim.x) {
+        int lo = 0, hi = bt.n_tracks;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (bt.frame_off[mid] <= f) lo = mid; else hi = mid;
+        }
+        const int track = lo;
+        const int64_t m_idx = f - bt.frame_off[track];
+        const int64_t s_begin = bt.sample_off[track];
+        const int64_t n_samp = bt.sample_off[track + 1] - s_begin;
+        const int64_t frames_k = bt.frame_off[track + 1] - bt.frame_off[track];
+        const int64_t start = m_idx * bt.hop - (bt.center_pad ? kNfft / 2 : 0);
+        const float *x = bt.audio + s_begin;
+
+        // ---- pass 1 ----
+        C v[16];
+        const bool interior = (start >= 0) && (start + kNfft <= n_samp);
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            const int64_t s = start + 256 * n1 + 2 * t;
+            float2 xv = make_float2(0.f, 0.f);
+            if (interior) xv = ld_stream_f2(x + s);
+            else {
+                if (s >= 0 && s < n_samp) xv.x = __ldg(x + s);
+                if (s + 1 >= 0 && s + 1 < n_samp) xv.y = __ldg(x + s + 1);
+            }
+            v[n1] = C{xv.x * win[2 * n1], xv.y * win[2 * n1 + 1]};
+        }
+        fft16(v);
+        sA[t] = v[0];
+#pragma unroll
+        for (int k1 = 1; k1 < 16; k1++) sA[k1 * kStrideA + t] = cmul(v[k1], tw1[k1]);
+        __syncthreads();
+        // ---- pass 2 ----
+        {
+            const int k1 = t >> 3, m2 = t & 7;
+#pragma unroll
+            for (int m1 = 0; m1 < 16; m1++) v[m1] = sA[k1 * kStrideA + 8 * m1 + m2];
+            fft16(v);
+            sB[k1 * kStrideB + m2] = v[0];
+#pragma unroll
+            for (int k2 = 1; k2 < 16; k2++) sB[k1 * kStrideB + k2 * 8 + m2] = cmul(v[k2], sTw2[k2 * 8 + m2]);
+        }
+        __syncthreads();
+        // ---- pass 3 ----
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int p = t + h * kThreads;
+            const int k1 = p & 15, k2 = p >> 4;
+            C u[8];
+#pragma unroll
+            for (int m2 = 0; m2 < 8; m2++) u[m2] = sB[k1 * kStrideB + k2 * 8 + m2];
+            fft8(u);
+#pragma unroll
+            for (int k3 = 0; k3 < 8; k3++) sA[k1 + 16 * k2 + 256 * k3] = u[k3];
+        }
+        __syncthreads();
+        // ---- untangle + power -> sP ----
+        {
+            constexpr float kc[8] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                                     0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f};
+            constexpr float ks[8] = {0.f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                                     0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f, 0.98078528040323044913f};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int k = t + kThreads * i;
+                if (k == 0) {
+                    const C z0 = sA[0];
+                    const float x0 = z0.x + z0.y, xn = z0.x - z0.y;
+                    const C zq = sA[1024];
+                    sP[0] = x0 * x0;
+                    sP[2048] = xn * xn;
+                    sP[1024] = zq.x * zq.x + zq.y * zq.y;
+                    sP[kZeroSlot] = 0.f;
+                } else {
+                    const C zk = sA[k], zn = sA[kNc - k];
+                    const C e = {0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y)};
+                    const C d = {0.5f * (zk.x - zn.x), 0.5f * (zk.y + zn.y)};
+                    const C wk = cmul(C{twu0.x, twu0.y}, C{kc[i], -ks[i]});       // W_4096^(t + 128 i)
+                    const C o = mul_mi(cmul(wk, d));
+                    const C xa = cadd(e, o), xb = csub(e, o);
+                    sP[k] = xa.x * xa.x + xa.y * xa.y;
+                    sP[kNc - k] = xb.x * xb.x + xb.y * xb.y;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- sparse filterbank: 6 statically indexed partial sums per thread ----
+        float acc[kWin];
+#pragma unroll
+        for (int w = 0; w < kWin; w++) acc[w] = 0.f;
+#pragma unroll 4
+        for (int i = 0; i < tb.bpt; i++) {
+            const float p = sP[__ldg(tb.paddr + i * kThreads + t)];
+            const float *wp = tb.wsp + (size_t)i * kWin * kThreads + t;
+#pragma unroll
+            for (int w = 0; w < kWin; w++) acc[w] = fmaf(__ldg(wp + w * kThreads), p, acc[w]);
+        }
+        float dacc = 0.f;
+        if (t >= kThreads - kChroma) {          // 12 threads: the wide low bins with all 12 weights
+            const int c = t - (kThreads - kChroma);
+            for (int j = 0; j < tb.nd; j++) dacc = fmaf(__ldg(tb.wdense + j * kChroma + c), sP[__ldg(tb.kdense + j)], dacc);
+        }
+#pragma unroll
+        for (int w = 0; w < kWin; w++) sRed[w * kThreads + t] = acc[w];
+        if (t >= kThreads - kChroma) sRed[kWin * kThreads + t - (kThreads - kChroma)] = dacc;
+        __syncthreads();
+        // ---- combine: (class c, window position w) sums over the threads whose window starts at c - w ----
+        if (t < kChroma * kWin) {
+            const int c = t / kWin, w = t - c * kWin;
+            int c0 = c - w;
+            if (c0 < 0) c0 += kChroma;
+            float sacc = 0.f;
+            for (int q = sCls[c0]; q < sCls[c0 + 1]; q++) sacc += sRed[w * kThreads + q];
+            sRed[kWin * kThreads + kChroma + t] = sacc;
+        }
+        __syncthreads();
+        if (t < 32) {
+            float raw = 0.f;
+            if (lane < kChroma) {
+                raw = sRed[kWin * kThreads + lane];
+#pragma unroll
+                for (int w = 0; w < kWin; w++) raw += sRed[kWin * kThreads + kChroma + lane * kWin + w];
+            }
+            float val = raw;
+            if (bt.normalize) {
+                float ss = raw * raw;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+                float len = sqrtf(ss);
+                if (len < FLT_MIN) len = 1.f;
+                val = raw / len;
+            }
+            if (lane < kChroma) {
+                const int64_t o = kChroma * bt.out_off[track] + (int64_t)lane * frames_k + m_idx;
+                if (bt.out_f64) static_cast<double *>(bt.out)[o] = (double)val;
+                else static_cast<float *>(bt.out)[o] = val;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 struct afs_chroma_plan {
@@ -268,6 +476,12 @@ struct afs_chroma_plan {
     Cx<double> *d_tw2048 = nullptr, *d_tw4096 = nullptr;
     int64_t *d_meta = nullptr;     // sample_off | frame_off | out_off
     int meta_cap = 0;
+    // fast-path tables (class-sorted sparse filterbank); fast_ok == false -> generic kernel only
+    bool fast_ok = false;
+    int bpt = 0, nd = 0;
+    float *f_wsp = nullptr, *f_wdense = nullptr;
+    uint16_t *u_paddr = nullptr, *u_kdense = nullptr;
+    int *i_cls = nullptr;
 };
 
 template <typename T> static size_t chroma_smem_bytes()
@@ -280,6 +494,76 @@ static int upload(T **dst, const std::vector<T> &src)
 {
     AFS_CUDA(cudaMalloc(dst, sizeof(T) * src.size()));
     AFS_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+    return AFS_OK;
+}
+
+
+// Derive the class-sorted sparse form of the filterbank (see chroma_fast_kernel).  fb is [k][12].
+static int build_fast_tables(afs_chroma_plan *pl, const std::vector<double> &fb)
+{
+    const double tol = 1e-6;
+    std::vector<int> c0(kBins, 0);
+    std::vector<int> dense;
+    std::vector<std::vector<int>> by_class(kChroma);
+    for (int k = 0; k < kBins; k++) {
+        const double *col = &fb[(size_t)k * kChroma];
+        double cmax = 0.0;
+        for (int c = 0; c < kChroma; c++) cmax = std::max(cmax, std::fabs(col[c]));
+        int best = 0;
+        double best_kept = -1.0;
+        for (int s = 0; s < kChroma; s++) {
+            double kept = 0.0;
+            for (int w = 0; w < kWin; w++) kept += col[(s + w) % kChroma] * col[(s + w) % kChroma];
+            if (kept > best_kept) { best_kept = kept; best = s; }
+        }
+        double dropped = 0.0;
+        for (int c = 0; c < kChroma; c++) {
+            const int rel = (c - best + kChroma) % kChroma;
+            if (rel >= kWin) dropped = std::max(dropped, std::fabs(col[c]));
+        }
+        c0[k] = best;
+        if (cmax > 0.0 && dropped > tol * cmax) dense.push_back(k);
+        else by_class[best].push_back(k);
+    }
+    if ((int)dense.size() > kMaxDense) return AFS_OK;        // structure absent: generic kernel only
+    int bpt = 0;
+    for (int cand = 8; cand <= kMaxBpt; cand++) {
+        int thr = 0;
+        for (int c = 0; c < kChroma; c++) thr += ((int)by_class[c].size() + cand - 1) / cand;
+        if (thr <= kThreads) { bpt = cand; break; }
+    }
+    if (!bpt) return AFS_OK;
+    std::vector<float> wsp((size_t)bpt * kWin * kThreads, 0.f);
+    std::vector<uint16_t> paddr((size_t)bpt * kThreads, (uint16_t)kZeroSlot);
+    std::vector<int> cls(kChroma + 1, 0);
+    int thr = 0;
+    for (int c = 0; c < kChroma; c++) {
+        cls[c] = thr;
+        const std::vector<int> &bins = by_class[c];
+        const int nthr = ((int)bins.size() + bpt - 1) / bpt;
+        for (size_t q = 0; q < bins.size(); q++) {
+            // deal bins round-robin over this class's threads: neighbouring bins -> neighbouring lanes
+            const int tt = thr + (int)(q % nthr), slot = (int)(q / nthr);
+            paddr[(size_t)slot * kThreads + tt] = (uint16_t)bins[q];
+            for (int w = 0; w < kWin; w++)
+                wsp[((size_t)slot * kWin + w) * kThreads + tt] = (float)fb[(size_t)bins[q] * kChroma + (c + w) % kChroma];
+        }
+        thr += nthr;
+    }
+    cls[kChroma] = thr;
+    std::vector<float> wdense(std::max<size_t>(1, dense.size() * kChroma), 0.f);
+    std::vector<uint16_t> kdense(std::max<size_t>(1, dense.size()), 0);
+    for (size_t j = 0; j < dense.size(); j++) {
+        kdense[j] = (uint16_t)dense[j];
+        for (int c = 0; c < kChroma; c++) wdense[j * kChroma + c] = (float)fb[(size_t)dense[j] * kChroma + c];
+    }
+    int rc = AFS_OK;
+    if ((rc = upload(&pl->f_wsp, wsp)) || (rc = upload(&pl->u_paddr, paddr)) || (rc = upload(&pl->i_cls, cls)) ||
+        (rc = upload(&pl->f_wdense, wdense)) || (rc = upload(&pl->u_kdense, kdense)))
+        return rc;
+    pl->bpt = bpt;
+    pl->nd = (int)dense.size();
+    pl->fast_ok = true;
     return AFS_OK;
 }
 
@@ -317,6 +601,10 @@ int afs_chroma_plan_create(afs_chroma_plan **out, const double *h_filterbank, in
         afs_chroma_plan_destroy(pl);
         return afs::fail(AFS_ERR_CUDA, "afs_chroma_plan_create: %s", cudaGetErrorString(e));
     }
+    if (int rc2 = build_fast_tables(pl, fb)) {
+        afs_chroma_plan_destroy(pl);
+        return rc2;
+    }
     *out = pl;
     return AFS_OK;
 }
@@ -327,6 +615,7 @@ int afs_chroma_plan_destroy(afs_chroma_plan *pl)
     cudaFree(pl->f_hann); cudaFree(pl->f_fb); cudaFree(pl->f_tw2048); cudaFree(pl->f_tw4096);
     cudaFree(pl->d_hann); cudaFree(pl->d_fb); cudaFree(pl->d_tw2048); cudaFree(pl->d_tw4096);
     cudaFree(pl->d_meta);
+    cudaFree(pl->f_wsp); cudaFree(pl->f_wdense); cudaFree(pl->u_paddr); cudaFree(pl->u_kdense); cudaFree(pl->i_cls);
     delete pl;
     return AFS_OK;
 }
@@ -399,6 +688,19 @@ extern "C" int afs_chroma_batch(afs_chroma_plan *pl, const float *d_audio, const
     bt.normalize = normalize;
     bt.out_f64 = out_dtype == AFS_F64;
     bt.out = d_out;
+    if (compute_dtype == AFS_F32 && pl->fast_ok) {
+        ChromaFastTables ft{pl->f_hann, reinterpret_cast<const float2 *>(pl->f_tw2048), reinterpret_cast<const float2 *>(pl->f_tw4096),
+                            pl->f_wsp, pl->u_paddr, pl->i_cls, pl->f_wdense, pl->u_kdense, pl->bpt, pl->nd};
+        int occ = 0;
+        AFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chroma_fast_kernel, kThreads, 0));
+        if (occ < 1) return afs::fail(AFS_ERR_CUDA, "chroma fast kernel does not fit on an SM");
+        int64_t blocks = (int64_t)afs::sm_count() * occ;
+        if (blocks > bt.total_frames) blocks = bt.total_frames;
+        chroma_fast_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(ft, bt);
+        afs::count_launch();
+        AFS_CUDA(cudaGetLastError());
+        return AFS_OK;
+    }
     if (compute_dtype == AFS_F32) {
         ChromaTables<float> tb{pl->f_hann, pl->f_tw2048, pl->f_tw4096, pl->f_fb};
         return launch_chroma<float>(tb, bt, st);
