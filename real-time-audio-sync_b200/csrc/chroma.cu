@@ -280,6 +280,7 @@ struct ChromaFastTables {
     const float *hann;          // 4096
     const float2 *tw2048;       // exp(-2 pi i j / 2048)
     const float2 *tw4096;       // exp(-2 pi i k / 4096), k <= 1024
+    const float2 *tw1;          // [15][128]: W_2048^(t k1) at [(k1-1)][t]
     const float *wsp;           // [bpt][6][128]
     const uint16_t *paddr;      // [bpt][128]
     const int *cls_start;       // [13] threads [cls_start[c], cls_start[c+1]) have window start c
@@ -295,26 +296,26 @@ __device__ __forceinline__ float2 ld_stream_f2(const float *p)
     return v;
 }
 
+constexpr int kFastStrideA = 129;   // odd row strides: 64-bit accesses whose lanes run along k1 are conflict free
+constexpr int kFastStrideB = 129;
+
 __global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFastTables tb, const ChromaBatch bt)
 {
     using C = Cx<float>;
-    __shared__ __align__(16) C sA[16 * kStrideA];          // pass-1 output; later Z in natural order; later reduction scratch
-    __shared__ __align__(16) C sB[16 * kStrideB];          // pass-2 output; later the power spectrum (float[2052])
+    __shared__ __align__(16) C sA[16 * kFastStrideA];      // pass-1 output; later Z in natural order; later reduction scratch
+    __shared__ __align__(16) C sB[16 * kFastStrideB];      // pass-2 output; later the power spectrum (float[2052])
     __shared__ C sTw2[16 * 8];                              // W_128^(m2 k2) at [k2][m2]
     __shared__ int sCls[13];
     const int t = threadIdx.x;
     const int lane = t & 31;
 
-    // ---- per-thread constants, loaded once ----
-    float win[32];
+    // per-thread constants for the whole persistent loop: 32 window values and 15 pass-1 twiddles
+    float2 win[16];
     C tw1[16];
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) {
-        win[2 * n1] = tb.hann[256 * n1 + 2 * t];
-        win[2 * n1 + 1] = tb.hann[256 * n1 + 2 * t + 1];
-    }
+    for (int n1 = 0; n1 < 16; n1++) win[n1] = reinterpret_cast<const float2 *>(tb.hann)[128 * n1 + t];
 #pragma unroll
-    for (int k1 = 1; k1 < 16; k1++) { const float2 w = tb.tw2048[t * k1]; tw1[k1] = C{w.x, w.y}; }
+    for (int k1 = 1; k1 < 16; k1++) { const float2 w = tb.tw1[(k1 - 1) * kThreads + t]; tw1[k1] = C{w.x, w.y}; }
     const float2 twu0 = tb.tw4096[t];                       // W_4096^t ; W_4096^(t + 128 i) = twu0 * W_32^i
     { const float2 w = tb.tw2048[16 * (t & 7) * (t >> 3)]; sTw2[t] = C{w.x, w.y}; }
     if (t < 13) sCls[t] = tb.cls_start[t];
@@ -322,13 +323,9 @@ __global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFa
     float *sRed = reinterpret_cast<float *>(sA);            // [6][128] + dense[12] + part[72]
     __syncthreads();
 
+    int track = 0;
     for (int64_t f = blockIdx.x; f < bt.total_frames; f += gridDim.x) {
-        int lo = 0, hi = bt.n_tracks;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (bt.frame_off[mid] <= f) lo = mid; else hi = mid;
-        }
-        const int track = lo;
+        while (bt.frame_off[track + 1] <= f) track++;       // frames are visited in increasing order
         const int64_t m_idx = f - bt.frame_off[track];
         const int64_t s_begin = bt.sample_off[track];
         const int64_t n_samp = bt.sample_off[track + 1] - s_begin;
@@ -336,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFa
         const int64_t start = m_idx * bt.hop - (bt.center_pad ? kNfft / 2 : 0);
         const float *x = bt.audio + s_begin;
 
-        // ---- pass 1 ----
+        // ---- pass 1: thread m = t ----
         C v[16];
         const bool interior = (start >= 0) && (start + kNfft <= n_samp);
 #pragma unroll
@@ -348,32 +345,32 @@ __global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFa
                 if (s >= 0 && s < n_samp) xv.x = __ldg(x + s);
                 if (s + 1 >= 0 && s + 1 < n_samp) xv.y = __ldg(x + s + 1);
             }
-            v[n1] = C{xv.x * win[2 * n1], xv.y * win[2 * n1 + 1]};
+            v[n1] = C{xv.x * win[n1].x, xv.y * win[n1].y};
         }
         fft16(v);
         sA[t] = v[0];
 #pragma unroll
-        for (int k1 = 1; k1 < 16; k1++) sA[k1 * kStrideA + t] = cmul(v[k1], tw1[k1]);
+        for (int k1 = 1; k1 < 16; k1++) sA[k1 * kFastStrideA + t] = cmul(v[k1], tw1[k1]);
         __syncthreads();
-        // ---- pass 2 ----
+        // ---- pass 2: thread (k1 = t % 16, m2 = t / 16) ----
         {
-            const int k1 = t >> 3, m2 = t & 7;
+            const int k1 = t & 15, m2 = t >> 4;
 #pragma unroll
-            for (int m1 = 0; m1 < 16; m1++) v[m1] = sA[k1 * kStrideA + 8 * m1 + m2];
+            for (int m1 = 0; m1 < 16; m1++) v[m1] = sA[k1 * kFastStrideA + 8 * m1 + m2];
             fft16(v);
-            sB[k1 * kStrideB + m2] = v[0];
+            sB[k1 * kFastStrideB + m2] = v[0];
 #pragma unroll
-            for (int k2 = 1; k2 < 16; k2++) sB[k1 * kStrideB + k2 * 8 + m2] = cmul(v[k2], sTw2[k2 * 8 + m2]);
+            for (int k2 = 1; k2 < 16; k2++) sB[k1 * kFastStrideB + k2 * 8 + m2] = cmul(v[k2], sTw2[k2 * 8 + m2]);
         }
         __syncthreads();
-        // ---- pass 3 ----
+        // ---- pass 3: (k1 = p % 16, k2 = p / 16), 8-point DFT over m2 ----
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int p = t + h * kThreads;
             const int k1 = p & 15, k2 = p >> 4;
             C u[8];
 #pragma unroll
-            for (int m2 = 0; m2 < 8; m2++) u[m2] = sB[k1 * kStrideB + k2 * 8 + m2];
+            for (int m2 = 0; m2 < 8; m2++) u[m2] = sB[k1 * kFastStrideB + k2 * 8 + m2];
             fft8(u);
 #pragma unroll
             for (int k3 = 0; k3 < 8; k3++) sA[k1 + 16 * k2 + 256 * k3] = u[k3];
@@ -480,6 +477,7 @@ struct afs_chroma_plan {
     bool fast_ok = false;
     int bpt = 0, nd = 0;
     float *f_wsp = nullptr, *f_wdense = nullptr;
+    Cx<float> *f_tw1 = nullptr;
     uint16_t *u_paddr = nullptr, *u_kdense = nullptr;
     int *i_cls = nullptr;
 };
@@ -557,7 +555,15 @@ static int build_fast_tables(afs_chroma_plan *pl, const std::vector<double> &fb)
         kdense[j] = (uint16_t)dense[j];
         for (int c = 0; c < kChroma; c++) wdense[j * kChroma + c] = (float)fb[(size_t)dense[j] * kChroma + c];
     }
+    std::vector<Cx<float>> tw1((size_t)15 * kThreads);
+    const double pi = 3.14159265358979323846;
+    for (int k1 = 1; k1 < 16; k1++)
+        for (int t = 0; t < kThreads; t++) {
+            const double ang = 2.0 * pi * (double)(t * k1) / kNc;
+            tw1[(size_t)(k1 - 1) * kThreads + t] = {(float)std::cos(ang), (float)-std::sin(ang)};
+        }
     int rc = AFS_OK;
+    if ((rc = upload(&pl->f_tw1, tw1))) return rc;
     if ((rc = upload(&pl->f_wsp, wsp)) || (rc = upload(&pl->u_paddr, paddr)) || (rc = upload(&pl->i_cls, cls)) ||
         (rc = upload(&pl->f_wdense, wdense)) || (rc = upload(&pl->u_kdense, kdense)))
         return rc;
@@ -615,7 +621,7 @@ int afs_chroma_plan_destroy(afs_chroma_plan *pl)
     cudaFree(pl->f_hann); cudaFree(pl->f_fb); cudaFree(pl->f_tw2048); cudaFree(pl->f_tw4096);
     cudaFree(pl->d_hann); cudaFree(pl->d_fb); cudaFree(pl->d_tw2048); cudaFree(pl->d_tw4096);
     cudaFree(pl->d_meta);
-    cudaFree(pl->f_wsp); cudaFree(pl->f_wdense); cudaFree(pl->u_paddr); cudaFree(pl->u_kdense); cudaFree(pl->i_cls);
+    cudaFree(pl->f_wsp); cudaFree(pl->f_wdense); cudaFree(pl->f_tw1); cudaFree(pl->u_paddr); cudaFree(pl->u_kdense); cudaFree(pl->i_cls);
     delete pl;
     return AFS_OK;
 }
@@ -690,7 +696,7 @@ extern "C" int afs_chroma_batch(afs_chroma_plan *pl, const float *d_audio, const
     bt.out = d_out;
     if (compute_dtype == AFS_F32 && pl->fast_ok) {
         ChromaFastTables ft{pl->f_hann, reinterpret_cast<const float2 *>(pl->f_tw2048), reinterpret_cast<const float2 *>(pl->f_tw4096),
-                            pl->f_wsp, pl->u_paddr, pl->i_cls, pl->f_wdense, pl->u_kdense, pl->bpt, pl->nd};
+                            reinterpret_cast<const float2 *>(pl->f_tw1), pl->f_wsp, pl->u_paddr, pl->i_cls, pl->f_wdense, pl->u_kdense, pl->bpt, pl->nd};
         int occ = 0;
         AFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chroma_fast_kernel, kThreads, 0));
         if (occ < 1) return afs::fail(AFS_ERR_CUDA, "chroma fast kernel does not fit on an SM");
