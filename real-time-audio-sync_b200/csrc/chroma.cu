@@ -323,18 +323,15 @@ __global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFa
     float *sRed = reinterpret_cast<float *>(sA);            // [6][128] + dense[12] + part[72]
     __syncthreads();
 
-    int track = 0;
-    for (int64_t f = blockIdx.x; f < bt.total_frames; f += gridDim.x) {
-        while (bt.frame_off[track + 1] <= f) track++;       // frames are visited in increasing order
-        const int64_t m_idx = f - bt.frame_off[track];
-        const int64_t s_begin = bt.sample_off[track];
-        const int64_t n_samp = bt.sample_off[track + 1] - s_begin;
-        const int64_t frames_k = bt.frame_off[track + 1] - bt.frame_off[track];
-        const int64_t start = m_idx * bt.hop - (bt.center_pad ? kNfft / 2 : 0);
+    // frame loader: audio of frame f (windowing applied later) -> 16 float2 registers
+    int ld_track = 0;
+    float2 xin[16];
+    auto load_frame = [&](int64_t f) {
+        while (bt.frame_off[ld_track + 1] <= f) ld_track++;          // frames are visited in increasing order
+        const int64_t s_begin = bt.sample_off[ld_track];
+        const int64_t n_samp = bt.sample_off[ld_track + 1] - s_begin;
+        const int64_t start = (f - bt.frame_off[ld_track]) * bt.hop - (bt.center_pad ? kNfft / 2 : 0);
         const float *x = bt.audio + s_begin;
-
-        // ---- pass 1: thread m = t ----
-        C v[16];
         const bool interior = (start >= 0) && (start + kNfft <= n_samp);
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) {
@@ -345,8 +342,21 @@ __global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFa
                 if (s >= 0 && s < n_samp) xv.x = __ldg(x + s);
                 if (s + 1 >= 0 && s + 1 < n_samp) xv.y = __ldg(x + s + 1);
             }
-            v[n1] = C{xv.x * win[n1].x, xv.y * win[n1].y};
+            xin[n1] = xv;
         }
+    };
+    if ((int64_t)blockIdx.x < bt.total_frames) load_frame(blockIdx.x);
+
+    int track = 0;
+    for (int64_t f = blockIdx.x; f < bt.total_frames; f += gridDim.x) {
+        while (bt.frame_off[track + 1] <= f) track++;
+        const int64_t m_idx = f - bt.frame_off[track];
+        const int64_t frames_k = bt.frame_off[track + 1] - bt.frame_off[track];
+
+        // ---- pass 1: thread m = t ----
+        C v[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) v[n1] = C{xin[n1].x * win[n1].x, xin[n1].y * win[n1].y};
         fft16(v);
         sA[t] = v[0];
 #pragma unroll
@@ -376,6 +386,8 @@ __global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFa
             for (int k3 = 0; k3 < 8; k3++) sA[k1 + 16 * k2 + 256 * k3] = u[k3];
         }
         __syncthreads();
+        // next frame's samples go in flight now; they land while the filterbank runs
+        if (f + gridDim.x < bt.total_frames) load_frame(f + gridDim.x);
         // ---- untangle + power -> sP ----
         {
             constexpr float kc[8] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
