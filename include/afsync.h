@@ -78,6 +78,28 @@ int afs_dtw_accumulate(afs_dtw_plan *plan, const void *d_a, const void *d_b, voi
 int afs_dtw_backtrack(afs_dtw_plan *plan, const void *d_workspace, int32_t *d_path,
                       int32_t *d_path_start, int32_t *d_path_len, void *stream);
 
+/* ---- K4: one very long pair split into column stripes, one stripe per GPU (BASELINE config[4]).
+ * No reference equivalent beyond the recurrence itself (dtw.py:32-40).  Each stripe is a single-pair
+ * fp64 plan of (M x N_g) over the stripe's own (12, N_g) slice of seq_b.  d_leftb[i] = acc_cost of the
+ * column left of the stripe (NULL for the first stripe); d_in_flag[band] != 0 once rows of that band
+ * are valid (NULL: all valid).  d_rightb / d_out_flag: where this stripe publishes its last column and
+ * raises the per-band flag for its right neighbour — normally memory of the NEXT GPU mapped with
+ * afs_ipc_open (stores travel over NVLink, flags are released at system scope); NULL on the last stripe. */
+int afs_dtw_accumulate_stripe(afs_dtw_plan *plan, const void *d_a, const void *d_b_stripe, void *d_workspace,
+                              double *d_acc_end, const double *d_leftb, const int *d_in_flag, double *d_rightb,
+                              int *d_out_flag, void *stream);
+/* Backtrack inside one stripe from (start_i, start_j) (stripe-local column).  Points are written
+ * back-to-front into d_path with global column = col0 + j.  d_out3 = {first valid index, count,
+ * exit row}: exit row is where the path continues in the left neighbour's last column, -1 at (0,0). */
+int afs_dtw_backtrack_stripe(afs_dtw_plan *plan, const void *d_workspace, int start_i, int start_j, int col0,
+                             int first_stripe, int32_t *d_path, int32_t *d_out3, void *stream);
+/* CUDA-IPC exchange blocks (zero-initialised): allocate + export a 64-byte handle / map a peer's block. */
+int afs_ipc_alloc(size_t bytes, void **d_ptr, void *handle64);
+int afs_ipc_open(const void *handle64, void **d_ptr);
+int afs_ipc_clear(void *d_ptr, size_t bytes, void *stream);
+int afs_ipc_close(void *d_ptr);
+int afs_ipc_free(void *d_ptr);
+
 /* ===================================================================== OTW family
  * Replaces OnlineTimeWarping.insert (otw_eran.py:38-85, eval_path_cost :215-239,
  * set_direction :153-188, best_point :192-211), LiveNoteV2.insert

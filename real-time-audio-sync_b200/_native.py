@@ -37,6 +37,13 @@ _SIGNATURES = {
     "afs_dtw_plan_path_layout": (C.c_int, [_vp, C.c_int, _i64p, _i64p]),
     "afs_dtw_accumulate": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "afs_dtw_backtrack": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "afs_dtw_accumulate_stripe": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "afs_dtw_backtrack_stripe": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "afs_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp), _vp]),
+    "afs_ipc_open": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "afs_ipc_clear": (C.c_int, [_vp, C.c_size_t, _vp]),
+    "afs_ipc_close": (C.c_int, [_vp]),
+    "afs_ipc_free": (C.c_int, [_vp]),
     "afs_otw_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _vp, _i64p, _i64p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "afs_otw_destroy": (C.c_int, [_vp]),
     "afs_otw_state_bytes": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),

@@ -111,6 +111,11 @@ struct DtwArgs {
     int *ticket;
     double *acc_end;
     T *dense_cost, *dense_acc;
+    // K4 (column stripe of one long pair; all null for ordinary batches)
+    const double *leftb;   // [M] acc of the column left of this stripe (null: this is the first stripe)
+    double *rightb;        // [M] out: acc of this stripe's last column (may be peer-mapped memory)
+    const int *in_flag;    // [nbands] raised by the left stripe when leftb rows of a band are valid (null: valid already)
+    int *out_flag;         // [nbands] raised for the right stripe (may be peer-mapped; null: none)
 };
 
 // Per-lane wavefront state.
@@ -296,10 +301,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
             for (int r = 0; r < kRows; r++) L.left[r] = A::inf();
             L.up_prev = A::inf();
             L.bottom = A::inf();
+            if (args.leftb != nullptr) {
+                // column stripe of a longer pair (K4): column -1 of this stripe is the last column of the
+                // stripe to the left.  Wait until that stripe (another GPU, or an earlier launch) has
+                // finished this band, then take acc[i, c0-1] as `left` and acc[i-1, c0-1] as the first diag.
+                if (args.in_flag != nullptr)
+                    while (afs::ld_acquire_sys(args.in_flag + band) == 0) __nanosleep(200);
+#pragma unroll
+                for (int r = 0; r < kRows; r++)
+                    if (r0 + r < pm.M) L.left[r] = (T)__ldcg(args.leftb + r0 + r);
+                if (r0 > 0 && r0 - 1 < pm.M) L.up_prev = (T)__ldcg(args.leftb + r0 - 1);
+            }
             // dtw.py:20-21: acc[0,0] = cost[0,0], back = 2.  A virtual diagonal neighbour of
             // -cost[0,0] makes (0,0) an ordinary cell: fma(2, c, -c) == c exactly, code 2; the
             // slot (up_prev) is overwritten right after, so nothing else ever sees it.
-            if (band == 0 && lane == 0) {
+            if (band == 0 && lane == 0 && args.leftb == nullptr) {
                 T s = A::mul(L.ar[0][0], __ldg(btp));
 #pragma unroll
                 for (int k = 1; k < kF; k++) s = A::fma(L.ar[0][k], __ldg(btp + k), s);
@@ -383,7 +399,52 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
                 args.acc_end[it.pair] = (double)e + base;
             }
         }
+        if (args.rightb != nullptr) {
+            // K4: hand the stripe's last column of this band to the stripe on the right (possibly
+            // peer-mapped memory of the next GPU over NVLink), then raise its flag at system scope
+            const int r0 = band * kBandRows + lane * kRows;
+#pragma unroll
+            for (int r = 0; r < kRows; r++)
+                if (r0 + r < pm.M) args.rightb[r0 + r] = (double)L.left[r] + base;
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0 && args.out_flag != nullptr) afs::st_release_sys(args.out_flag + band, 1);
+        }
     }
+}
+
+// K3 for one stripe of a column-striped pair: walk from (i0, j0) (stripe-local column) until the
+// path leaves the stripe through its left edge (or reaches (0,0) in the first stripe).  Points are
+// written back-to-front with GLOBAL column indices (col0 + j).  exit_i = row at which the walk
+// continues in the stripe to the left (its last column), or -1 when (0,0) was reached.
+__global__ void dtw_backtrack_stripe_kernel(const DtwPair *pairs, const uint4 *dir, int i0, int j0, int col0, int first,
+                                            int32_t *path, int32_t *out3)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const DtwPair pm = pairs[0];
+    const uint8_t *dbytes = reinterpret_cast<const uint8_t *>(dir + pm.dir_off);
+    int2 *out = reinterpret_cast<int2 *>(path) + pm.path_off;
+    int i = i0, j = j0;
+    int pos = pm.path_cap - 1;
+    int exit_i = -1;
+    out[pos] = make_int2(i, j + col0);
+    for (;;) {
+        if (first && i == 0 && j == 0) break;
+        const int g = i >> 2;
+        const int jj = j + (g & 31);
+        const int64_t unit = (int64_t)(jj >> 4) * pm.gpad + g;
+        const uint32_t byte = dbytes[unit * 16 + (jj & 15)];
+        const uint32_t code = (byte >> (2 * (i & 3))) & 3u;
+        if (code == 0) j -= 1;
+        else if (code == 1) i -= 1;
+        else { i -= 1; j -= 1; }
+        if (j < 0) { exit_i = i; break; }
+        pos -= 1;
+        out[pos] = make_int2(i, j + col0);
+    }
+    out3[0] = pos;
+    out3[1] = pm.path_cap - pos;
+    out3[2] = exit_i;
 }
 
 // K3: backtrack over the direction map (dtw.py:43-52).  One warp per pair; lane 0
@@ -533,7 +594,8 @@ int afs_dtw_plan_path_layout(const afs_dtw_plan *pl, int pair, int64_t *offset, 
 
 template <typename T>
 static int launch_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b, void *ws, double *d_acc_end,
-                             void *dense_cost, void *dense_acc, cudaStream_t st)
+                             void *dense_cost, void *dense_acc, cudaStream_t st, const double *leftb = nullptr,
+                             double *rightb = nullptr, const int *in_flag = nullptr, int *out_flag = nullptr)
 {
     char *base = static_cast<char *>(ws);
     DtwArgs<T> args;
@@ -550,6 +612,10 @@ static int launch_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b,
     args.acc_end = d_acc_end;
     args.dense_cost = static_cast<T *>(dense_cost);
     args.dense_acc = static_cast<T *>(dense_acc);
+    args.leftb = leftb;
+    args.rightb = rightb;
+    args.in_flag = in_flag;
+    args.out_flag = out_flag;
     AFS_CUDA(cudaMemsetAsync(args.prog, 0, pl->prog_bytes, st));
     {
         const int threads = 128;
@@ -589,6 +655,74 @@ int afs_dtw_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b, void 
     if (pl->dtype == AFS_F64)
         return launch_accumulate<double>(pl, d_a, d_b, d_workspace, d_acc_end, d_dense_cost, d_dense_acc, st);
     return launch_accumulate<float>(pl, d_a, d_b, d_workspace, d_acc_end, d_dense_cost, d_dense_acc, st);
+}
+
+int afs_dtw_accumulate_stripe(afs_dtw_plan *pl, const void *d_a, const void *d_b_stripe, void *d_workspace,
+                              double *d_acc_end, const double *d_leftb, const int *d_in_flag, double *d_rightb,
+                              int *d_out_flag, void *stream)
+{
+    if (!pl || !d_a || !d_b_stripe || !d_workspace || !d_acc_end)
+        return afs::fail(AFS_ERR_INVALID, "afs_dtw_accumulate_stripe: null argument");
+    if (pl->n_pairs != 1 || pl->dtype != AFS_F64)
+        return afs::fail(AFS_ERR_UNSUPPORTED, "afs_dtw_accumulate_stripe: needs a single-pair fp64 plan (M x stripe columns)");
+    return launch_accumulate<double>(pl, d_a, d_b_stripe, d_workspace, d_acc_end, nullptr, nullptr,
+                                     static_cast<cudaStream_t>(stream), d_leftb, d_rightb, d_in_flag, d_out_flag);
+}
+
+int afs_dtw_backtrack_stripe(afs_dtw_plan *pl, const void *d_workspace, int start_i, int start_j, int col0,
+                             int first_stripe, int32_t *d_path, int32_t *d_out3, void *stream)
+{
+    if (!pl || !d_workspace || !d_path || !d_out3) return afs::fail(AFS_ERR_INVALID, "afs_dtw_backtrack_stripe: null argument");
+    if (pl->n_pairs != 1) return afs::fail(AFS_ERR_UNSUPPORTED, "afs_dtw_backtrack_stripe: single-pair plan only");
+    if (start_i < 0 || start_i >= pl->pairs[0].M || start_j < 0 || start_j >= pl->pairs[0].N)
+        return afs::fail(AFS_ERR_INVALID, "afs_dtw_backtrack_stripe: start cell outside the stripe");
+    dtw_backtrack_stripe_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        pl->d_pairs, static_cast<const uint4 *>(d_workspace), start_i, start_j, col0, first_stripe, d_path, d_out3);
+    afs::count_launch();
+    AFS_CUDA(cudaGetLastError());
+    return AFS_OK;
+}
+
+// ---- CUDA IPC helpers: an exchange block (boundary column + flags) one process allocates and its
+// right-hand neighbour rank maps, so that the stripe kernel can store into it over NVLink ----
+int afs_ipc_alloc(size_t bytes, void **d_ptr, void *handle64)
+{
+    if (!d_ptr || !handle64 || bytes == 0) return afs::fail(AFS_ERR_INVALID, "afs_ipc_alloc: bad argument");
+    AFS_CUDA(cudaMalloc(d_ptr, bytes));
+    AFS_CUDA(cudaMemset(*d_ptr, 0, bytes));
+    cudaIpcMemHandle_t h;
+    AFS_CUDA(cudaIpcGetMemHandle(&h, *d_ptr));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    return AFS_OK;
+}
+
+int afs_ipc_open(const void *handle64, void **d_ptr)
+{
+    if (!d_ptr || !handle64) return afs::fail(AFS_ERR_INVALID, "afs_ipc_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    AFS_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return AFS_OK;
+}
+
+int afs_ipc_clear(void *d_ptr, size_t bytes, void *stream)
+{
+    if (!d_ptr) return afs::fail(AFS_ERR_INVALID, "afs_ipc_clear: null pointer");
+    AFS_CUDA(cudaMemsetAsync(d_ptr, 0, bytes, static_cast<cudaStream_t>(stream)));
+    return AFS_OK;
+}
+
+int afs_ipc_close(void *d_ptr)
+{
+    if (d_ptr) AFS_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return AFS_OK;
+}
+
+int afs_ipc_free(void *d_ptr)
+{
+    if (d_ptr) AFS_CUDA(cudaFree(d_ptr));
+    return AFS_OK;
 }
 
 int afs_dtw_backtrack(afs_dtw_plan *pl, const void *d_workspace, int32_t *d_path, int32_t *d_path_start,
