@@ -449,31 +449,59 @@ __global__ void dtw_backtrack_stripe_kernel(const DtwPair *pairs, const uint4 *d
 
 // K3: backtrack over the direction map (dtw.py:43-52).  One warp per pair; lane 0
 // walks, writing the path back-to-front so that no reversal pass is needed.
-__global__ void dtw_backtrack_kernel(const DtwPair *pairs, int n_pairs, const uint4 *dir, int32_t *path,
-                                     int32_t *path_start, int32_t *path_len)
+// The walk is a chain of dependent loads; to keep HBM latency off that chain the warp stages a
+// whole tile of the direction map — one band (128 rows) x 128 skewed columns = 8 x 512 contiguous
+// bytes — into shared memory with coalesced 16-byte loads, and lane 0 then walks inside the tile
+// (>= ~100 steps per tile on a diagonal-ish path).
+constexpr int kBtWarps = 2;
+__global__ void __launch_bounds__(kBtWarps * 32) dtw_backtrack_kernel(const DtwPair *pairs, int n_pairs, const uint4 *dir,
+                                                                      int32_t *path, int32_t *path_start, int32_t *path_len)
 {
-    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (p >= n_pairs || (threadIdx.x & 31) != 0) return;
+    __shared__ uint4 s_tile[kBtWarps][8 * 32];        // [cbp & 7][g & 31]
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * kBtWarps + w;
+    if (p >= n_pairs) return;
     const DtwPair pm = pairs[p];
-    const uint8_t *dbytes = reinterpret_cast<const uint8_t *>(dir + pm.dir_off);
+    const uint4 *dunits = dir + pm.dir_off;
+    const uint8_t *tb = reinterpret_cast<const uint8_t *>(s_tile[w]);
     int2 *out = reinterpret_cast<int2 *>(path) + pm.path_off;
+    const int ncbp = pm.nsteps >> 4;
     int i = pm.M - 1, j = pm.N - 1;
     int pos = pm.path_cap - 1;
-    out[pos] = make_int2(i, j);
-    while (i > 0 || j > 0) {
-        const int g = i >> 2;
-        const int jj = j + (g & 31);
-        const int64_t unit = (int64_t)(jj >> 4) * pm.gpad + g;
-        const uint32_t byte = dbytes[unit * 16 + (jj & 15)];
-        const uint32_t code = (byte >> (2 * (i & 3))) & 3u;
-        if (code == 0) j -= 1;
-        else if (code == 1) i -= 1;
-        else { i -= 1; j -= 1; }
-        pos -= 1;
-        out[pos] = make_int2(i, j);
+    if (lane == 0) out[pos] = make_int2(i, j);
+    while (i > 0 || j > 0) {                          // uniform: lane 0's (i, j) is broadcast below
+        const int band = i >> 7;
+        const int cb8 = (j + ((i >> 2) & 31)) >> 7;   // block of 8 skewed column units
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int cbp = cb8 * 8 + q;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (cbp < ncbp) v = __ldcs(dunits + (int64_t)cbp * pm.gpad + band * 32 + lane);
+            s_tile[w][q * 32 + lane] = v;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            while (i > 0 || j > 0) {
+                const int g = i >> 2;
+                const int jj = j + (g & 31);
+                if ((i >> 7) != band || (jj >> 7) != cb8) break;
+                const uint32_t byte = tb[(((jj >> 4) & 7) * 32 + (g & 31)) * 16 + (jj & 15)];
+                const uint32_t code = (byte >> (2 * (i & 3))) & 3u;
+                if (code == 0) j -= 1;
+                else if (code == 1) i -= 1;
+                else { i -= 1; j -= 1; }
+                pos -= 1;
+                out[pos] = make_int2(i, j);
+            }
+        }
+        i = __shfl_sync(0xffffffffu, i, 0);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        pos = __shfl_sync(0xffffffffu, pos, 0);
     }
-    path_start[p] = pos;
-    path_len[p] = pm.path_cap - pos;
+    if (lane == 0) {
+        path_start[p] = pos;
+        path_len[p] = pm.path_cap - pos;
+    }
 }
 
 }  // namespace
