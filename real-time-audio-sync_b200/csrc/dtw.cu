@@ -463,7 +463,6 @@ __global__ void __launch_bounds__(kBtWarps * 32) dtw_backtrack_kernel(const DtwP
     if (p >= n_pairs) return;
     const DtwPair pm = pairs[p];
     const uint4 *dunits = dir + pm.dir_off;
-    const uint8_t *tb = reinterpret_cast<const uint8_t *>(s_tile[w]);
     int2 *out = reinterpret_cast<int2 *>(path) + pm.path_off;
     const int ncbp = pm.nsteps >> 4;
     int i = pm.M - 1, j = pm.N - 1;
@@ -485,13 +484,20 @@ __global__ void __launch_bounds__(kBtWarps * 32) dtw_backtrack_kernel(const DtwP
                 const int g = i >> 2;
                 const int jj = j + (g & 31);
                 if ((i >> 7) != band || (jj >> 7) != cb8) break;
-                const uint32_t byte = tb[(((jj >> 4) & 7) * 32 + (g & 31)) * 16 + (jj & 15)];
-                const uint32_t code = (byte >> (2 * (i & 3))) & 3u;
-                if (code == 0) j -= 1;
-                else if (code == 1) i -= 1;
-                else { i -= 1; j -= 1; }
-                pos -= 1;
-                out[pos] = make_int2(i, j);
+                // one 16-byte unit (4 rows x 16 skewed columns) into registers; walk inside it with bit ops only
+                const uint4 u = s_tile[w][((jj >> 4) & 7) * 32 + (g & 31)];
+                const uint64_t lo = (uint64_t)u.x | ((uint64_t)u.y << 32), hi = (uint64_t)u.z | ((uint64_t)u.w << 32);
+                int cs = jj & 15, r = i & 3;
+                for (;;) {
+                    const uint64_t sel = (cs & 8) ? hi : lo;
+                    const uint32_t code = (uint32_t)(sel >> (((cs & 7) << 3) + 2 * r)) & 3u;
+                    const int di = code != 0u, dj = code != 1u;      // 0: left, 1: up, 2: diag
+                    i -= di; r -= di;
+                    j -= dj; cs -= dj;
+                    pos -= 1;
+                    out[pos] = make_int2(i, j);
+                    if (r < 0 || cs < 0 || (i | j) == 0) break;
+                }
             }
         }
         i = __shfl_sync(0xffffffffu, i, 0);
