@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFa
             fft8(u);
 #pragma unroll
             for (int k3 = 0; k3 < 8; k3++) sA[k1 + 16 * k2 + 256 * k3] = u[k3];
+            if (p == 0) sA[kNc] = u[0];        // Z[2048] == Z[0]: makes k = 0 an ordinary pair in the untangle
         }
         __syncthreads();
         // next frame's samples go in flight now; they land while the filterbank runs
@@ -396,25 +397,20 @@ __global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFa
                                      0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f, 0.98078528040323044913f};
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const int k = t + kThreads * i;
-                if (k == 0) {
-                    const C z0 = sA[0];
-                    const float x0 = z0.x + z0.y, xn = z0.x - z0.y;
-                    const C zq = sA[1024];
-                    sP[0] = x0 * x0;
-                    sP[2048] = xn * xn;
-                    sP[1024] = zq.x * zq.x + zq.y * zq.y;
-                    sP[kZeroSlot] = 0.f;
-                } else {
-                    const C zk = sA[k], zn = sA[kNc - k];
-                    const C e = {0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y)};
-                    const C d = {0.5f * (zk.x - zn.x), 0.5f * (zk.y + zn.y)};
-                    const C wk = cmul(C{twu0.x, twu0.y}, C{kc[i], -ks[i]});       // W_4096^(t + 128 i)
-                    const C o = mul_mi(cmul(wk, d));
-                    const C xa = cadd(e, o), xb = csub(e, o);
-                    sP[k] = xa.x * xa.x + xa.y * xa.y;
-                    sP[kNc - k] = xb.x * xb.x + xb.y * xb.y;
-                }
+                const int k = t + kThreads * i;            // 0 .. 1023, partner 2048 - k
+                const C zk = sA[k], zn = sA[kNc - k];
+                const C e = {0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y)};
+                const C d = {0.5f * (zk.x - zn.x), 0.5f * (zk.y + zn.y)};
+                const C wk = cmul(C{twu0.x, twu0.y}, C{kc[i], -ks[i]});       // W_4096^(t + 128 i)
+                const C o = mul_mi(cmul(wk, d));
+                const C xa = cadd(e, o), xb = csub(e, o);
+                sP[k] = xa.x * xa.x + xa.y * xa.y;
+                sP[kNc - k] = xb.x * xb.x + xb.y * xb.y;
+            }
+            if (t == 0) {
+                const C zq = sA[1024];                     // X[1024] = conj(Z[1024])
+                sP[1024] = zq.x * zq.x + zq.y * zq.y;
+                sP[kZeroSlot] = 0.f;
             }
         }
         __syncthreads();
