@@ -215,5 +215,53 @@ def main():
         print("%-24s %8d bytes" % (f, os.path.getsize(os.path.join(HERE, f))))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--eval-only" not in sys.argv:
     main()
+
+
+def make_eval_golden():
+    """Score the reference's own DTW path of the chopin_20b pair with the reference's own scorer
+    (tests.py:29-137, class test_simple), loaded through the shim up to the point where the script
+    starts evaluating at import time."""
+    import io, re, types, contextlib
+    src = open(os.path.join(ref_shim.REFERENCE_ROOT, "tests.py")).read()
+    src = src[: src.index("params = {")]
+    src = src[src.index("def lines_from_file"):]
+    src = re.sub(r"^(\s*)print (.+)$", r"\1print(\2)", src, flags=re.M)
+    mod = types.ModuleType("_ref_tests_head")
+    mod.__dict__["csv"] = __import__("csv")
+    exec(compile(src, "tests.py", "exec"), mod.__dict__)
+    paths = np.load(os.path.join(HERE, "chopin_paths.npz"))
+    ref_wav, live_wav = ref_shim.song(REF_WAV), ref_shim.song(LIVE_WAV)
+    out = {}
+    cases = {k: paths[k] for k in ("dtw_path", "otw_c50", "ln2_c50", "wtw_path")}
+    shifted = paths["dtw_path"].copy()
+    shifted[:, 1] = np.clip(shifted[:, 1] - 45, 0, None)        # a deliberately bad path (ref lags ~4 s)
+    cases["dtw_shifted45"] = shifted
+    out["shift"] = 45
+    for key, pth in cases.items():
+        scorer = mod.test_simple(ref_wav, live_wav, [tuple(p) for p in pth.tolist()])
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            ret = scorer.get_error()
+        printed = [float(l.split(":")[1].strip().split()[0]) for l in buf.getvalue().splitlines() if l.startswith("Percent incorrect")]
+        out[key] = {"returned": ret, "printed": printed}
+    # the two ground-truth CSVs are data fixtures (19 rows each)
+    for name in ("chopin_rubinstein_20b.csv", "chopin_rachmaninoff_20b.csv"):
+        shutil.copyfile(ref_shim.song("chopin/" + name), os.path.join(HERE, name))
+    # and one field log as a format fixture (tests.py:20-27 reader)
+    log = sorted(f for f in os.listdir(os.path.join(ref_shim.REFERENCE_ROOT, "tests")) if f.startswith("livenote_test_live_"))
+    sizes = [(os.path.getsize(os.path.join(ref_shim.REFERENCE_ROOT, "tests", f)), f) for f in log]
+    sizes = [x for x in sizes if x[0] > 200]
+    pick = min(sizes)[1]
+    shutil.copyfile(os.path.join(ref_shim.REFERENCE_ROOT, "tests", pick), os.path.join(HERE, "field_log_sample.txt"))
+    out["field_log_points"] = len(mod.data_from_file(os.path.join(HERE, "field_log_sample.txt")))
+    out["field_log_first"] = list(mod.data_from_file(os.path.join(HERE, "field_log_sample.txt"))[0])
+    import json
+    with open(os.path.join(HERE, "eval_golden.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+    print(out)
+
+
+if __name__ == "__main__":
+    make_eval_golden()

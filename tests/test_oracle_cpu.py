@@ -181,3 +181,36 @@ def test_oracle_vs_live_reference_wtw_end_to_end(orc):
             break
     gold = [tuple(map(int, l.split())) for l in open(shim.song("chopin/tests/wtw_test_20b.txt")) if l.strip()]
     assert w.path == gold
+
+
+# ---------------------------------------------------------------- evaluation glue, CPU only
+def test_beat_scorer_matches_reference_scorer(entry, paths):
+    import json
+    ev = entry.submodule("evalutil")
+    gold = json.load(open(os.path.join(GOLD, "eval_golden.json")))
+    sc = ev.BeatScorer(os.path.join(GOLD, "chopin_rubinstein_20b.csv"), os.path.join(GOLD, "chopin_rachmaninoff_20b.csv"))
+    cases = {k: paths[k] for k in ("dtw_path", "otw_c50", "ln2_c50", "wtw_path")}
+    shifted = paths["dtw_path"].copy()
+    shifted[:, 1] = np.clip(shifted[:, 1] - gold["shift"], 0, None)
+    cases["dtw_shifted45"] = shifted
+    for key, pth in cases.items():
+        got = sc.score([tuple(p) for p in pth.tolist()])
+        want = gold[key]["printed"]
+        mine = [got["pct_off_%d_beats" % t] for t in (1, 3, 5, 10)] + [got["pct_off_%d_secs" % t] for t in (1, 3, 5, 10)]
+        assert np.allclose(mine, want, rtol=0, atol=1e-12), key
+        assert abs(sc.get_error([tuple(p) for p in pth.tolist()]) - gold[key]["returned"]) < 1e-12
+    assert gold["dtw_shifted45"]["returned"] > 0          # the bad path really scores badly
+
+
+def test_path_log_round_trip(entry, tmp_path, paths):
+    import json
+    ev = entry.submodule("evalutil")
+    gold = json.load(open(os.path.join(GOLD, "eval_golden.json")))
+    log = ev.read_path_log(os.path.join(GOLD, "field_log_sample.txt"))       # a log the reference's live app wrote
+    assert len(log) == gold["field_log_points"] and list(log[0]) == gold["field_log_first"]
+    out = os.path.join(str(tmp_path), "log.txt")
+    pth = [tuple(p) for p in paths["otw_c50"].tolist()]
+    ev.write_path_log(out, "Songs/chopin/chopin_rubinstein_20b.wav", 4096, 2048, {"search_band_width": 50, "max_run_count": 3}, pth)
+    raw = open(out, "rb").read()
+    assert raw.count(b"\r\n") == 5 + len(pth) and raw.startswith(b"Songs/chopin/chopin_rubinstein_20b.wav\r\nfft_len: 4096\r\n")
+    assert ev.read_path_log(out) == pth
