@@ -16,10 +16,12 @@
 //            4-slot shared-memory ring per warp, and a lane fetches its column with
 //            128-bit shared loads at a compile-time stride (bank-conflict free);
 //   band b needs the last row of band b-1: it is streamed through an L2-resident
-//   ring of two rows per pair in chunks of 32 columns, guarded by a release/acquire
-//   progress counter per band.  Bands are claimed from one global atomic ticket in
-//   an order where every dependency has a smaller ticket (band-major, pairs
-//   interleaved), so a waiting warp always waits on a warp that is already running.
+//   ring of two rows per pair in chunks of 32 columns.  Each hand-off record validates
+//   itself ({value lo32, tag, value hi32, tag}, tag = launch epoch | band; one 128-bit
+//   volatile store / load): no flags, no fences, no L1 invalidation on the hot path.
+//   Bands are claimed from one global atomic ticket in an order where every dependency
+//   has a smaller ticket (band-major, pairs interleaved), so a waiting warp always
+//   waits on a warp that is already running.
 //
 // Direction map layout (per pair): 16-byte units; unit (cbp, g) covers row group
 // g = i >> 2 (4 rows) and 16 consecutive SKEWED columns  jj = j + (g & 31),
@@ -105,9 +107,9 @@ struct DtwArgs {
     const DtwItem *items;
     int n_items;
     uint4 *dir;
-    double *brow;     // band hand-off rows: absolute accumulated costs, always fp64
+    uint4 *brow;      // band hand-off rows: {value lo32, tag, value hi32, tag} records (absolute fp64 costs)
+    uint32_t epoch;   // 1..250, different for consecutive launches on the same workspace
     T *bt;
-    int *prog;
     int *ticket;
     double *acc_end;
     T *dense_cost, *dense_acc;
@@ -153,6 +155,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
                      : "r"(smem_u32(bar)), "r"(parity)
                      : "memory");
     } while (!done);
+}
+
+// hand-off records are read/written with single 128-bit volatile accesses (never cached in L1)
+__device__ __forceinline__ uint4 ld_record(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_record(uint4 *p, uint4 v)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 template <typename T>
@@ -270,10 +284,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
         const bool feeds_next = band + 1 < pm.nbands;
         const T *ap = args.a + pm.a_off;
         const T *btp = args.bt + pm.bt_off;
-        double *brow_cur = args.brow + pm.brow_off + (int64_t)(band & 1) * pm.nsteps;
-        const double *brow_prev = args.brow + pm.brow_off + (int64_t)((band + 1) & 1) * pm.nsteps;
-        int *prog_cur = args.prog + pm.prog_off + band;
-        const int *prog_prev = prog_cur - 1;
+        uint4 *brow_cur = args.brow + pm.brow_off + (int64_t)(band & 1) * pm.nsteps;
+        const uint4 *brow_prev = args.brow + pm.brow_off + (int64_t)((band + 1) & 1) * pm.nsteps;
+        // tag = launch epoch (1..250, changes every launch) | band: a stale record of the previous launch or of
+        // band-2 in the same ring slot can never be mistaken for the one this band waits for
+        const uint32_t tag_cur = (args.epoch << 24) | (uint32_t)band;
+        const uint32_t tag_prev = (args.epoch << 24) | (uint32_t)(band - 1);
         uint4 *dirp = args.dir + pm.dir_off + (int64_t)band * 32 + lane;
         const int nchunks = pm.nchunks;
 
@@ -329,6 +345,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
         // steps (min-plus recurrences are shift invariant), so offsets stay O(band height) and the
         // accumulated cost keeps ~1e-7 relative accuracy over 4e4 additions.  fp64 mode: base == 0.
         double base = 0.0;
+        uint4 pref = make_uint4(0u, 0u, 0u, 0u);
         uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
         for (int s0 = 0; s0 < pm.nsteps; s0 += 32) {
             const int c0 = s0 >> 5;
@@ -355,15 +372,31 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
             __syncwarp();                      // all lanes are done with chunk c0-2 (same slot as c0+2)
             stage(c0 + 2);
             if (band > 0 && s0 < N) {
-                // wait until the band above has published columns [s0, s0+32)
-                const int need = min(s0 + 32, N);
-                while (afs::ld_acquire(prog_prev) < need) __nanosleep(40);
+                // Columns [s0, s0+32) of the band above.  Every hand-off record validates itself: the two
+                // halves of the fp64 value each travel with the producer band's tag, so one 128-bit load
+                // either shows both tags (value complete) or is retried — no flag, no fence, no L1 flush.
                 const int col = s0 + lane;
-                if (sizeof(T) == 4 && s0 == 0) base = __ldcg(brow_prev);       // start from the level of the row above
-                T v = (col < N) ? (T)(__ldcg(brow_prev + col) - base) : A::inf();
+                const bool want = col < N;
+                uint4 rec = pref;                 // issued one group ago (all zero before the first group)
+                bool ok = !want || ((rec.y == tag_prev) && (rec.w == tag_prev));
+                for (;;) {
+                    if (!ok) {
+                        rec = ld_record(brow_prev + col);
+                        ok = (rec.y == tag_prev) && (rec.w == tag_prev);
+                    }
+                    if (__all_sync(full, ok)) break;
+                    __nanosleep(20);
+                }
+                const double vabs = __hiloint2double((int)rec.z, (int)rec.x);
+                if (sizeof(T) == 4 && s0 == 0) base = __shfl_sync(full, vabs, 0);   // start from the level of the row above
+                T v = want ? (T)(vabs - base) : A::inf();
                 __syncwarp();
                 sm.ubuf[lane] = v;
                 __syncwarp();
+                // next group's record goes in flight now and is checked in 32 steps; if the band above is
+                // not that far ahead yet the check fails and the poll loop above takes over
+                pref = make_uint4(0u, 0u, 0u, 0u);
+                if (col + 32 < N) pref = ld_record(brow_prev + col + 32);
             }
 #pragma unroll 1
             for (int g4 = 0; g4 < 8; g4++) {
@@ -383,10 +416,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
                 // slots 0..31 hold lane 31's columns s0-31 .. s0
                 __syncwarp();
                 const int col = s0 - 31 + lane;
-                if (col >= 0 && col < N) __stcg(brow_cur + col, (double)sm.obuf[lane] + base);
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) afs::st_release(prog_cur, min(s0 + 1, N));
+                if (col >= 0 && col < N) {
+                    const double vabs = (double)sm.obuf[lane] + base;
+                    st_record(brow_cur + col, make_uint4((uint32_t)__double2loint(vabs), tag_cur, (uint32_t)__double2hiint(vabs), tag_cur));
+                }
+                __syncwarp();      // obuf is rewritten by lane 31 in the next group
             }
         }
         // after the sweep every lane's left[] holds column N-1: acc_cost[M-1, N-1] sits in one of them
@@ -520,6 +554,8 @@ struct afs_dtw_plan {
     DtwPair *d_pairs = nullptr;
     DtwItem *d_items = nullptr;
     size_t dir_bytes = 0, brow_bytes = 0, bt_bytes = 0, prog_bytes = 0;
+    uint32_t epoch = 0;
+    const void *last_ws = nullptr;      // workspace whose hand-off area has been cleared once
     int64_t total_path = 0;
     int total_bands = 0;
     int max_cols_pad = 0;
@@ -578,9 +614,9 @@ int afs_dtw_plan_create(afs_dtw_plan **out, int n_pairs, const int64_t *h_len_a,
     pl->total_bands = prog;
     pl->total_path = path_pairs;
     pl->dir_bytes = afs::align_up((size_t)dir_units * 16, 256);
-    pl->brow_bytes = afs::align_up((size_t)brow_elems * sizeof(double), 256);
+    pl->brow_bytes = afs::align_up((size_t)brow_elems * sizeof(uint4), 256);
     pl->bt_bytes = afs::align_up((size_t)bt_elems * esz, 256);
-    pl->prog_bytes = afs::align_up((size_t)(prog + 1) * sizeof(int), 256);
+    pl->prog_bytes = 256;      // the band ticket
     cudaError_t e = cudaMalloc(&pl->d_pairs, sizeof(DtwPair) * n_pairs);
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_items, sizeof(DtwItem) * pl->items.size());
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_pairs, pl->pairs.data(), sizeof(DtwPair) * n_pairs, cudaMemcpyHostToDevice);
@@ -639,10 +675,16 @@ static int launch_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b,
     args.items = pl->d_items;
     args.n_items = (int)pl->items.size();
     args.dir = reinterpret_cast<uint4 *>(base);
-    args.brow = reinterpret_cast<double *>(base + pl->dir_bytes);
+    args.brow = reinterpret_cast<uint4 *>(base + pl->dir_bytes);
     args.bt = reinterpret_cast<T *>(base + pl->dir_bytes + pl->brow_bytes);
-    args.prog = reinterpret_cast<int *>(base + pl->dir_bytes + pl->brow_bytes + pl->bt_bytes);
-    args.ticket = args.prog + pl->total_bands;
+    args.ticket = reinterpret_cast<int *>(base + pl->dir_bytes + pl->brow_bytes + pl->bt_bytes);
+    if (pl->last_ws != ws) {
+        // first use of this workspace: no stale bytes may look like a valid hand-off record
+        AFS_CUDA(cudaMemsetAsync(args.brow, 0, pl->brow_bytes, st));
+        pl->last_ws = ws;
+    }
+    pl->epoch = pl->epoch % 250u + 1u;
+    args.epoch = pl->epoch;
     args.acc_end = d_acc_end;
     args.dense_cost = static_cast<T *>(dense_cost);
     args.dense_acc = static_cast<T *>(dense_acc);
@@ -650,7 +692,7 @@ static int launch_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b,
     args.rightb = rightb;
     args.in_flag = in_flag;
     args.out_flag = out_flag;
-    AFS_CUDA(cudaMemsetAsync(args.prog, 0, pl->prog_bytes, st));
+    AFS_CUDA(cudaMemsetAsync(args.ticket, 0, pl->prog_bytes, st));
     {
         const int threads = 128;
         dim3 grid((pl->max_cols_pad + threads - 1) / threads, pl->n_pairs);
