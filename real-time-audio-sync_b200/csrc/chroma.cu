@@ -299,53 +299,56 @@ __device__ __forceinline__ float2 ld_stream_f2(const float *p)
 constexpr int kFastStrideA = 129;   // odd row strides: 64-bit accesses whose lanes run along k1 are conflict free
 constexpr int kFastStrideB = 129;
 
-__global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFastTables tb, const ChromaBatch bt)
+__global__ void __launch_bounds__(kThreads, 4) chroma_fast_kernel(const ChromaFastTables tb, const ChromaBatch bt)
 {
     using C = Cx<float>;
-    __shared__ __align__(16) C sA[16 * kFastStrideA];      // pass-1 output; later Z in natural order; later reduction scratch
-    __shared__ __align__(16) C sB[16 * kFastStrideB];      // pass-2 output; later the power spectrum (float[2052])
+    __shared__ __align__(128) C sA[16 * kFastStrideA];     // staged audio of the NEXT frame (16 KB, TMA) | pass-1 output | Z natural
+    __shared__ __align__(16) C sB[16 * kFastStrideB];      // pass-2 output; later power spectrum float[2052] + reduction scratch
     __shared__ C sTw2[16 * 8];                              // W_128^(m2 k2) at [k2][m2]
     __shared__ int sCls[13];
+    __shared__ __align__(8) uint64_t sBar;                  // completion of the staged-audio bulk copy
     const int t = threadIdx.x;
     const int lane = t & 31;
 
-    // per-thread constants for the whole persistent loop: 32 window values and 15 pass-1 twiddles
+    // per-thread constants for the whole persistent loop: 32 window values; pass-1 twiddles W^(t k1) are
+    // kept for k1 = 1, 2, 4, 8 only (the other eleven are products of those: 44 extra flops, 22 fewer registers)
     float2 win[16];
-    C tw1[16];
 #pragma unroll
     for (int n1 = 0; n1 < 16; n1++) win[n1] = reinterpret_cast<const float2 *>(tb.hann)[128 * n1 + t];
-#pragma unroll
-    for (int k1 = 1; k1 < 16; k1++) { const float2 w = tb.tw1[(k1 - 1) * kThreads + t]; tw1[k1] = C{w.x, w.y}; }
+    C w1, w2, w4, w8;
+    { const float2 a = tb.tw1[0 * kThreads + t], b = tb.tw1[1 * kThreads + t], c = tb.tw1[3 * kThreads + t], d = tb.tw1[7 * kThreads + t];
+      w1 = C{a.x, a.y}; w2 = C{b.x, b.y}; w4 = C{c.x, c.y}; w8 = C{d.x, d.y}; }
     const float2 twu0 = tb.tw4096[t];                       // W_4096^t ; W_4096^(t + 128 i) = twu0 * W_32^i
     { const float2 w = tb.tw2048[16 * (t & 7) * (t >> 3)]; sTw2[t] = C{w.x, w.y}; }
     if (t < 13) sCls[t] = tb.cls_start[t];
+    if (t == 0) {
+        afs::mbar_init(&sBar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     float *sP = reinterpret_cast<float *>(sB);
-    float *sRed = reinterpret_cast<float *>(sA);            // [6][128] + dense[12] + part[72]
+    float *sRed = sP + 2112;                                // [6][128] window sums + dense[12] + (class, w)[72]; sP ends at 2050
     __syncthreads();
 
-    // frame loader: audio of frame f (windowing applied later) -> 16 float2 registers
+    // Stage the 4096 samples of frame f (16 KB, contiguous) into sA with ONE TMA bulk copy when the frame lies
+    // inside the track and is 16-byte aligned; otherwise pass 1 reads it with guarded global loads.
     int ld_track = 0;
-    float2 xin[16];
-    auto load_frame = [&](int64_t f) {
+    auto stage_frame = [&](int64_t f) -> bool {
         while (bt.frame_off[ld_track + 1] <= f) ld_track++;          // frames are visited in increasing order
         const int64_t s_begin = bt.sample_off[ld_track];
         const int64_t n_samp = bt.sample_off[ld_track + 1] - s_begin;
         const int64_t start = (f - bt.frame_off[ld_track]) * bt.hop - (bt.center_pad ? kNfft / 2 : 0);
-        const float *x = bt.audio + s_begin;
-        const bool interior = (start >= 0) && (start + kNfft <= n_samp);
-#pragma unroll
-        for (int n1 = 0; n1 < 16; n1++) {
-            const int64_t s = start + 256 * n1 + 2 * t;
-            float2 xv = make_float2(0.f, 0.f);
-            if (interior) xv = ld_stream_f2(x + s);
-            else {
-                if (s >= 0 && s < n_samp) xv.x = __ldg(x + s);
-                if (s + 1 >= 0 && s + 1 < n_samp) xv.y = __ldg(x + s + 1);
-            }
-            xin[n1] = xv;
+        const float *src = bt.audio + s_begin + start;
+        const bool ok = (start >= 0) && (start + kNfft <= n_samp) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        if (ok && t == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            afs::mbar_expect_tx(&sBar, kNfft * sizeof(float));
+            afs::bulk_g2s(sA, src, kNfft * sizeof(float), &sBar);
         }
+        return ok;
     };
-    if ((int64_t)blockIdx.x < bt.total_frames) load_frame(blockIdx.x);
+    bool staged = ((int64_t)blockIdx.x < bt.total_frames) ? stage_frame(blockIdx.x) : false;
+    uint32_t bar_phase = 0;
 
     int track = 0;
     for (int64_t f = blockIdx.x; f < bt.total_frames; f += gridDim.x) {
@@ -355,12 +358,50 @@ __global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFa
 
         // ---- pass 1: thread m = t ----
         C v[16];
+        if (staged) {
+            afs::mbar_wait(&sBar, bar_phase);
+            bar_phase ^= 1u;
+            const float2 *xs = reinterpret_cast<const float2 *>(sA);
 #pragma unroll
-        for (int n1 = 0; n1 < 16; n1++) v[n1] = C{xin[n1].x * win[n1].x, xin[n1].y * win[n1].y};
+            for (int n1 = 0; n1 < 16; n1++) {
+                const float2 xv = xs[128 * n1 + t];
+                v[n1] = C{xv.x * win[n1].x, xv.y * win[n1].y};
+            }
+        } else {
+            const int64_t s_begin = bt.sample_off[track];
+            const int64_t n_samp = bt.sample_off[track + 1] - s_begin;
+            const int64_t start = m_idx * bt.hop - (bt.center_pad ? kNfft / 2 : 0);
+            const float *x = bt.audio + s_begin;
+#pragma unroll
+            for (int n1 = 0; n1 < 16; n1++) {
+                const int64_t s = start + 256 * n1 + 2 * t;
+                float2 xv = make_float2(0.f, 0.f);
+                if (s >= 0 && s < n_samp) xv.x = __ldg(x + s);
+                if (s + 1 >= 0 && s + 1 < n_samp) xv.y = __ldg(x + s + 1);
+                v[n1] = C{xv.x * win[n1].x, xv.y * win[n1].y};
+            }
+        }
         fft16(v);
-        sA[t] = v[0];
-#pragma unroll
-        for (int k1 = 1; k1 < 16; k1++) sA[k1 * kFastStrideA + t] = cmul(v[k1], tw1[k1]);
+        __syncthreads();                 // every thread has taken its samples out of sA
+        {
+            const C w3 = cmul(w2, w1), w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+            sA[t] = v[0];
+            sA[1 * kFastStrideA + t] = cmul(v[1], w1);
+            sA[2 * kFastStrideA + t] = cmul(v[2], w2);
+            sA[3 * kFastStrideA + t] = cmul(v[3], w3);
+            sA[4 * kFastStrideA + t] = cmul(v[4], w4);
+            sA[5 * kFastStrideA + t] = cmul(v[5], w5);
+            sA[6 * kFastStrideA + t] = cmul(v[6], w6);
+            sA[7 * kFastStrideA + t] = cmul(v[7], w7);
+            sA[8 * kFastStrideA + t] = cmul(v[8], w8);
+            sA[9 * kFastStrideA + t] = cmul(v[9], cmul(w8, w1));
+            sA[10 * kFastStrideA + t] = cmul(v[10], cmul(w8, w2));
+            sA[11 * kFastStrideA + t] = cmul(v[11], cmul(w8, w3));
+            sA[12 * kFastStrideA + t] = cmul(v[12], cmul(w8, w4));
+            sA[13 * kFastStrideA + t] = cmul(v[13], cmul(w8, w5));
+            sA[14 * kFastStrideA + t] = cmul(v[14], cmul(w8, w6));
+            sA[15 * kFastStrideA + t] = cmul(v[15], cmul(w8, w7));
+        }
         __syncthreads();
         // ---- pass 2: thread (k1 = t % 16, m2 = t / 16) ----
         {
@@ -387,8 +428,6 @@ __global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFa
             if (p == 0) sA[kNc] = u[0];        // Z[2048] == Z[0]: makes k = 0 an ordinary pair in the untangle
         }
         __syncthreads();
-        // next frame's samples go in flight now; they land while the filterbank runs
-        if (f + gridDim.x < bt.total_frames) load_frame(f + gridDim.x);
         // ---- untangle + power -> sP ----
         {
             constexpr float kc[8] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
@@ -414,6 +453,8 @@ __global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFa
             }
         }
         __syncthreads();
+        // sA is dead now: the next frame's samples are bulk-copied into it while the filterbank runs
+        staged = (f + gridDim.x < bt.total_frames) ? stage_frame(f + gridDim.x) : false;
         // ---- sparse filterbank: 6 statically indexed partial sums per thread ----
         float acc[kWin];
 #pragma unroll
@@ -466,7 +507,8 @@ __global__ void __launch_bounds__(kThreads, 3) chroma_fast_kernel(const ChromaFa
                 else static_cast<float *>(bt.out)[o] = val;
             }
         }
-        __syncthreads();
+        // no barrier here: the reduction scratch lives in sB, which is next written in pass 2 — two
+        // barriers away; pass 1 of the next frame only touches sA
     }
 }
 
