@@ -111,19 +111,16 @@ def default_plan():
 def chroma_batch(tracks, center=True, normalize=True, compute="fp32"):
     """Many tracks in one launch: list of 1-D sample arrays -> list of (12, frames) float64 arrays."""
     plan = default_plan()
-    lens = [len(t) + (len(t) & 1) for t in tracks]                 # even offsets (8-byte aligned float2 loads)
+    # every track starts on a 16-byte boundary (TMA bulk staging of whole frames); the zero padding at a
+    # track's end can at most add one frame, which is dropped below (frames are counted on the true length)
+    lens = [(len(t) + 3) // 4 * 4 for t in tracks]
     offs = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
     flat = np.zeros(int(offs[-1]), dtype=np.float32)
-    ends = []
     for k, t in enumerate(tracks):
         flat[offs[k] : offs[k] + len(t)] = np.asarray(t, dtype=np.float32)
-        ends.append(offs[k] + len(t))
-    # padded sample (if any) must not create an extra frame: pass true ends through per-track offsets
     d_audio = torch.from_numpy(flat).to(plan.device)
     outs = []
-    # tracks whose length is odd would see one padding zero; frames are counted on the true length
-    true_offs = offs.copy()
-    d_out, foffs = plan.run(d_audio, true_offs, center=center, normalize=normalize, out_dtype=torch.float64, compute=compute)
+    d_out, foffs = plan.run(d_audio, offs, center=center, normalize=normalize, out_dtype=torch.float64, compute=compute)
     host = d_out.cpu().numpy()
     for k, t in enumerate(tracks):
         nfr = plan.num_frames(len(t), center)

@@ -289,13 +289,6 @@ struct ChromaFastTables {
     int bpt, nd;
 };
 
-__device__ __forceinline__ float2 ld_stream_f2(const float *p)
-{
-    float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-    return v;
-}
-
 constexpr int kFastStrideA = 129;   // odd row strides: 64-bit accesses whose lanes run along k1 are conflict free
 constexpr int kFastStrideB = 129;
 
@@ -523,6 +516,7 @@ struct afs_chroma_plan {
     Cx<double> *d_tw2048 = nullptr, *d_tw4096 = nullptr;
     int64_t *d_meta = nullptr;     // sample_off | frame_off | out_off
     int meta_cap = 0;
+    std::vector<int64_t> h_meta;   // host copy of the per-batch offsets
     // fast-path tables (class-sorted sparse filterbank); fast_ok == false -> generic kernel only
     bool fast_ok = false;
     int bpt = 0, nd = 0;
@@ -711,7 +705,10 @@ extern "C" int afs_chroma_batch(afs_chroma_plan *pl, const float *d_audio, const
     if ((out_dtype != AFS_F32 && out_dtype != AFS_F64) || (compute_dtype != AFS_F32 && compute_dtype != AFS_F64))
         return afs::fail(AFS_ERR_INVALID, "afs_chroma_batch: bad dtype");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    std::vector<int64_t> meta((size_t)3 * n_tracks + 2);
+    // the host copy lives in the plan: it must stay valid until the async copy below has been staged,
+    // whatever kind of host memory the runtime takes it for (one batch in flight per plan)
+    std::vector<int64_t> &meta = pl->h_meta;
+    meta.assign((size_t)3 * n_tracks + 2, 0);
     int64_t *s_off = meta.data(), *f_off = s_off + n_tracks + 1, *o_off = f_off + n_tracks + 1;
     f_off[0] = 0;
     for (int k = 0; k < n_tracks; k++) {
@@ -730,7 +727,6 @@ extern "C" int afs_chroma_batch(afs_chroma_plan *pl, const float *d_audio, const
         AFS_CUDA(cudaMalloc(&pl->d_meta, sizeof(int64_t) * meta.size()));
         pl->meta_cap = (int)meta.size();
     }
-    // pageable source: the copy is staged before the call returns, so `meta` may go out of scope
     AFS_CUDA(cudaMemcpyAsync(pl->d_meta, meta.data(), sizeof(int64_t) * meta.size(), cudaMemcpyHostToDevice, st));
     ChromaBatch bt;
     bt.audio = d_audio;
