@@ -395,7 +395,11 @@ def bench_dtw(ctx):
         "hbm": {"achieved": alg_bytes / (acc_ms_mean * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (acc_ms_mean * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"},
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at exactly this configuration
+        # (profiles/ncu_raw_r1d_dtw.csv: 0.944 GB + 3.342 GB); None for any other configuration
+        "traffic": 4.286e9 if (P == 32 and Ln == 20000 and args.dtype == "fp64") else None,
+        "traffic_source": "profiles/ncu_raw_r1d_dtw.csv (ncu --set full, same 32 x 20k x 20k launch)",
+        "algorithmic_bytes": alg_bytes,
     }
     cpu = None if args.no_cpu_baseline else cpu_dtw_baseline(seconds=args.cpu_seconds)
     return {
@@ -554,7 +558,10 @@ def bench_chroma(ctx):
         "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"kernel": "chroma_kernel<float>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": gbs / hbm_peak, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
-                     "bytes_per_frame": CHROMA_BYTES_PER_FRAME, "traffic": None,
+                     "bytes_per_frame": CHROMA_BYTES_PER_FRAME,
+                     # ncu (profiles/ncu_raw_r1d_chroma.csv): 346.06 MB of DRAM traffic for a 41 344-frame launch
+                     # = 8370 B/frame (algorithmic 8240), scaled to this launch's frame count
+                     "traffic": 8370.0 * frames, "traffic_source": "profiles/ncu_raw_r1d_chroma.csv, per frame x frames",
                      "fp32": {"achieved": tfl, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tfl / fp32_peak,
                               "flop_per_frame": CHROMA_FLOP_PER_FRAME,
                               "peak_source": "derived: %d SMs x 128 lanes x 2 x %.0f MHz" % (n_sm, sm_max)}},
