@@ -71,15 +71,27 @@ template <> struct Arith<double> {
     static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-    static __device__ __forceinline__ void load_col(const double *p, double (&bk)[kF])
+    // one packed column (12 values) from shared memory: 6 x ld.shared.v2.f64 at immediate offsets
+    static __device__ __forceinline__ void load_col(uint32_t saddr, double (&bk)[kF])
     {
-#pragma unroll
-        for (int q = 0; q < kF / 2; q++) {
-            const double2 v = reinterpret_cast<const double2 *>(p)[q];
-            bk[2 * q] = v.x;
-            bk[2 * q + 1] = v.y;
-        }
+        lds2<0>(saddr, bk[0], bk[1]);
+        lds2<16>(saddr, bk[2], bk[3]);
+        lds2<32>(saddr, bk[4], bk[5]);
+        lds2<48>(saddr, bk[6], bk[7]);
+        lds2<64>(saddr, bk[8], bk[9]);
+        lds2<80>(saddr, bk[10], bk[11]);
     }
+    template <int OFF> static __device__ __forceinline__ void lds2(uint32_t saddr, double &x, double &y)
+    {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(x), "=d"(y) : "r"(saddr), "n"(OFF));
+    }
+    static __device__ __forceinline__ double lds(uint32_t saddr)
+    {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
+        return v;
+    }
+    static __device__ __forceinline__ void sts(uint32_t saddr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(saddr), "d"(v) : "memory"); }
 };
 template <> struct Arith<float> {
     static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
@@ -87,17 +99,23 @@ template <> struct Arith<float> {
     static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-    static __device__ __forceinline__ void load_col(const float *p, float (&bk)[kF])
+    static __device__ __forceinline__ void load_col(uint32_t saddr, float (&bk)[kF])
     {
-#pragma unroll
-        for (int q = 0; q < kF / 4; q++) {
-            const float4 v = reinterpret_cast<const float4 *>(p)[q];
-            bk[4 * q] = v.x;
-            bk[4 * q + 1] = v.y;
-            bk[4 * q + 2] = v.z;
-            bk[4 * q + 3] = v.w;
-        }
+        lds4<0>(saddr, bk[0], bk[1], bk[2], bk[3]);
+        lds4<16>(saddr, bk[4], bk[5], bk[6], bk[7]);
+        lds4<32>(saddr, bk[8], bk[9], bk[10], bk[11]);
     }
+    template <int OFF> static __device__ __forceinline__ void lds4(uint32_t saddr, float &x, float &y, float &z, float &w)
+    {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(saddr), "n"(OFF));
+    }
+    static __device__ __forceinline__ float lds(uint32_t saddr)
+    {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+        return v;
+    }
+    static __device__ __forceinline__ void sts(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
 };
 
 template <typename T>
@@ -194,7 +212,8 @@ __global__ void dtw_pack_b_kernel(const T *__restrict__ b, T *__restrict__ bt, c
 
 template <typename T, bool DENSE, int U>
 __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane, const int band, const DtwPair &pm,
-                                         WarpSmem<T> &sm, const bool feeds_next, uint32_t &dw, const DtwArgs<T> &args, const double base)
+                                         const uint32_t ring_s, const uint32_t ubuf_s, const uint32_t obuf_s, const bool feeds_next,
+                                         uint32_t &dw, const DtwArgs<T> &args, const double base)
 {
     using A = Arith<T>;
     constexpr int S = ColStride<T>::value;
@@ -204,12 +223,12 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
     // inputs for the lane's first row: value under the previous lane's last row, one step ago;
     // lane 0 takes it from the band above (staged in ubuf)
     T up = __shfl_up_sync(full, L.bottom, 1);
-    if (lane == 0) up = sm.ubuf[s & 31];
+    if (lane == 0) up = A::lds(ubuf_s + (s & 31) * (int)sizeof(T));
     if ((unsigned)j < (unsigned)N) {
         T c[kRows];
         {
             T bk[kF];
-            A::load_col(sm.ring + (j & (kRingSlots * kChunkCols - 1)) * S, bk);
+            A::load_col(ring_s + (j & (kRingSlots * kChunkCols - 1)) * (S * (int)sizeof(T)), bk);
 #pragma unroll
             for (int r = 0; r < kRows; r++) c[r] = A::mul(L.ar[r][0], bk[0]);
 #pragma unroll
@@ -247,7 +266,7 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
         L.up_prev = up;
         L.bottom = L.left[kRows - 1];
         dw |= nib << (8 * U);
-        if (feeds_next && lane == 31) sm.obuf[s & 31] = L.bottom;
+        if (feeds_next && lane == 31) A::sts(obuf_s + (s & 31) * (int)sizeof(T), L.bottom);
     }
 }
 
@@ -261,6 +280,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
     WarpSmem<T> &sm = reinterpret_cast<WarpSmem<T> *>(s_dyn)[w];
+    // 32-bit shared-space addresses for the per-step accesses (keeps address arithmetic out of the hot loop)
+    const uint32_t ring_s = smem_u32(sm.ring), ubuf_s = smem_u32(sm.ubuf), obuf_s = smem_u32(sm.obuf);
     const unsigned full = 0xffffffffu;
 
     if (lane == 0) {
@@ -402,10 +423,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
             for (int g4 = 0; g4 < 8; g4++) {
                 const int s = s0 + g4 * 4;
                 uint32_t dw = 0;
-                dtw_step<T, DENSE, 0>(L, s + 0, lane, band, pm, sm, feeds_next, dw, args, base);
-                dtw_step<T, DENSE, 1>(L, s + 1, lane, band, pm, sm, feeds_next, dw, args, base);
-                dtw_step<T, DENSE, 2>(L, s + 2, lane, band, pm, sm, feeds_next, dw, args, base);
-                dtw_step<T, DENSE, 3>(L, s + 3, lane, band, pm, sm, feeds_next, dw, args, base);
+                dtw_step<T, DENSE, 0>(L, s + 0, lane, band, pm, ring_s, ubuf_s, obuf_s, feeds_next, dw, args, base);
+                dtw_step<T, DENSE, 1>(L, s + 1, lane, band, pm, ring_s, ubuf_s, obuf_s, feeds_next, dw, args, base);
+                dtw_step<T, DENSE, 2>(L, s + 2, lane, band, pm, ring_s, ubuf_s, obuf_s, feeds_next, dw, args, base);
+                dtw_step<T, DENSE, 3>(L, s + 3, lane, band, pm, ring_s, ubuf_s, obuf_s, feeds_next, dw, args, base);
                 d0 = d1; d1 = d2; d2 = d3; d3 = dw;
                 if ((g4 & 3) == 3) {
                     const int cbp = s >> 4;

@@ -34,3 +34,21 @@ def test_striped_random_and_ties(striped, orc):
     acc_end, path = striped.dtw_striped_local(ea, eb, 3)
     _, oend, opath = orc.DTW(ea, eb, dense=False)
     assert acc_end == oend and np.array_equal(path, opath)
+
+
+def test_striped_two_gpus_peer_memory_handoff():
+    """One stripe per GPU, boundary columns stored straight into the neighbour's memory (CUDA IPC over
+    NVLink) while both kernels run; path and acc_end must equal the oracle's.  Needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29600 + (os.getpid() % 300)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tools", "striped_dist.py"), "3000", "4100", "check"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "PARITY path True" in out.stdout, out.stdout[-2000:]
