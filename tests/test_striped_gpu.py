@@ -51,4 +51,4 @@ def test_striped_two_gpus_peer_memory_handoff():
            "--master-port", str(port), os.path.join(root, "tools", "striped_dist.py"), "3000", "4100", "check"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
-    assert "PARITY path True" in out.stdout, out.stdout[-2000:]
+    assert "PARITY path True acc_end True" in out.stdout, out.stdout[-2000:]

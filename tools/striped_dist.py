@@ -31,6 +31,8 @@ t0 = time.perf_counter()
 path = sd.backtrack()
 t_bt = time.perf_counter() - t0
 end = sd.acc_end()
+end_all = torch.tensor([end if end is not None else 0.0], dtype=torch.float64, device="cuda")
+dist.all_reduce(end_all)            # only the last rank contributes a non-zero value
 if rank == world - 1:
     print("rank", rank, "acc_end", end, "accumulate s", [round(t, 4) for t in times], "GCUPS", round(M * N / min(times) / 1e9, 1), flush=True)
 if rank == 0:
@@ -38,6 +40,6 @@ if rank == 0:
     if check:
         from oracle import afs_oracle as orc
         _, oend, opath = orc.DTW(a, b, dense=False)
-        print("PARITY path", bool(np.array_equal(path, opath)), "oracle acc_end", oend, flush=True)
+        print("PARITY path", bool(np.array_equal(path, opath)), "acc_end", bool(float(end_all.item()) == oend), "oracle acc_end", oend, flush=True)
 sd.close()
 dist.destroy_process_group()
