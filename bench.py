@@ -280,6 +280,8 @@ def bench_striped(ctx):
         dist.barrier()
         if it > 0:
             times.append(time.perf_counter() - t0)
+    sd.backtrack()                       # first call also sets up NCCL's point-to-point channels
+    dist.barrier()
     t0 = time.perf_counter()
     path = sd.backtrack()
     t_bt = time.perf_counter() - t0

@@ -472,34 +472,64 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
 // path leaves the stripe through its left edge (or reaches (0,0) in the first stripe).  Points are
 // written back-to-front with GLOBAL column indices (col0 + j).  exit_i = row at which the walk
 // continues in the stripe to the left (its last column), or -1 when (0,0) was reached.
-__global__ void dtw_backtrack_stripe_kernel(const DtwPair *pairs, const uint4 *dir, int i0, int j0, int col0, int first,
-                                            int32_t *path, int32_t *out3)
+__global__ void __launch_bounds__(32) dtw_backtrack_stripe_kernel(const DtwPair *pairs, const uint4 *dir, int i0, int j0, int col0,
+                                                                  int first, int32_t *path, int32_t *out3)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // same tile-staged, register-decoded walk as dtw_backtrack_kernel (below), one warp
+    __shared__ uint4 s_tile[8 * 32];
+    const int lane = threadIdx.x;
     const DtwPair pm = pairs[0];
-    const uint8_t *dbytes = reinterpret_cast<const uint8_t *>(dir + pm.dir_off);
+    const uint4 *dunits = dir + pm.dir_off;
     int2 *out = reinterpret_cast<int2 *>(path) + pm.path_off;
+    const int ncbp = pm.nsteps >> 4;
     int i = i0, j = j0;
     int pos = pm.path_cap - 1;
     int exit_i = -1;
-    out[pos] = make_int2(i, j + col0);
-    for (;;) {
-        if (first && i == 0 && j == 0) break;
-        const int g = i >> 2;
-        const int jj = j + (g & 31);
-        const int64_t unit = (int64_t)(jj >> 4) * pm.gpad + g;
-        const uint32_t byte = dbytes[unit * 16 + (jj & 15)];
-        const uint32_t code = (byte >> (2 * (i & 3))) & 3u;
-        if (code == 0) j -= 1;
-        else if (code == 1) i -= 1;
-        else { i -= 1; j -= 1; }
-        if (j < 0) { exit_i = i; break; }
-        pos -= 1;
-        out[pos] = make_int2(i, j + col0);
+    int done = (first && i == 0 && j == 0) ? 1 : 0;
+    if (lane == 0) out[pos] = make_int2(i, j + col0);
+    while (!done) {
+        const int band = i >> 7;
+        const int cb8 = (j + ((i >> 2) & 31)) >> 7;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int cbp = cb8 * 8 + q;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (cbp < ncbp) v = __ldcs(dunits + (int64_t)cbp * pm.gpad + band * 32 + lane);
+            s_tile[q * 32 + lane] = v;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            while (!done) {
+                const int g = i >> 2;
+                const int jj = j + (g & 31);
+                if ((i >> 7) != band || (jj >> 7) != cb8) break;
+                const uint4 u = s_tile[((jj >> 4) & 7) * 32 + (g & 31)];
+                const uint64_t lo = (uint64_t)u.x | ((uint64_t)u.y << 32), hi = (uint64_t)u.z | ((uint64_t)u.w << 32);
+                int cs = jj & 15, r = i & 3;
+                for (;;) {
+                    const uint64_t sel = (cs & 8) ? hi : lo;
+                    const uint32_t code = (uint32_t)(sel >> (((cs & 7) << 3) + 2 * r)) & 3u;
+                    const int di = code != 0u, dj = code != 1u;      // 0: left, 1: up, 2: diag
+                    i -= di; r -= di;
+                    j -= dj; cs -= dj;
+                    if (j < 0) { exit_i = i; done = 1; break; }      // continues in the stripe to the left
+                    pos -= 1;
+                    out[pos] = make_int2(i, j + col0);
+                    if (first && (i | j) == 0) { done = 1; break; }
+                    if (r < 0 || cs < 0) break;
+                }
+            }
+        }
+        i = __shfl_sync(0xffffffffu, i, 0);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        done = __shfl_sync(0xffffffffu, done, 0);
+        __syncwarp();
     }
-    out3[0] = pos;
-    out3[1] = pm.path_cap - pos;
-    out3[2] = exit_i;
+    if (lane == 0) {
+        out3[0] = pos;
+        out3[1] = pm.path_cap - pos;
+        out3[2] = exit_i;
+    }
 }
 
 // K3: backtrack over the direction map (dtw.py:43-52).  One warp per pair; lane 0
