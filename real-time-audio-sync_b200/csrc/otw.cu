@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kOtwWarps * 32) otw_step_kernel(const OtwArgs 
                 S.t += 1;
                 if (S.t >= Lcap) {
                     status = AFS_STEP_FULL;    // otw_eran.py:53-55: live buffer exhausted, returns None forever
-                    if (S.t > Lcap) S.t = Lcap;
+                                               // (t keeps counting, exactly like the reference's self.t)
                 } else {
                     if (lane < kF) lh[(int64_t)(S.t % rs) * kF + lane] = fr[lane];
                     __syncwarp();
