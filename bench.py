@@ -692,13 +692,23 @@ def bench_otw(ctx):
         return None
     cpu = None if args.no_cpu_baseline else cpu_otw_baseline()
     o = res["otw"]
+    peaks = load_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # ncu (profiles/ncu_raw_r1d_otw.csv): 831 MB of DRAM traffic for one step of 4096 streams at c = 500 — the
+    # reference and live windows (c x 96 B each) are re-read every step and do not fit L2 for 4096 streams
+    traffic = 831.2e6 * S / 4096.0
+    otw_roof = {"kernel": "otw_step_kernel", "bound": "hbm", "achieved": traffic / (o["kernel_ms_mean"] * 1e-3) / 1e9,
+                "peak": hbm_peak, "unit": "GB/s", "frac": traffic / (o["kernel_ms_mean"] * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "measured" if "hbm_gbs" in peaks else "fallback", "traffic": traffic,
+                "traffic_source": "profiles/ncu_raw_r1d_otw.csv (one step, 4096 streams), scaled by stream count",
+                "note": "the metric is latency; the step is a chain of <= 5 serial sweeps per stream on top of this traffic"}
     return {
         "metric": "otw_p99_frame_latency_ms", "value": o["p99_ms"], "unit": "ms", "n_gpus": world, "higher_is_better": False,
         "steps": o["steps"], "warmup": OTW_C + 100, "ms_per_step": o["p50_ms"], "scaling": "weak", "dtype": "f64", "data": "synthetic", "vs_baseline": None,
         "config": {"workload": "online OTW (otw_eran) streaming alignment, %d concurrent streams per GPU, c=%d, max_run_count=3, ref %d frames (BASELINE cfg[3])" % (S, OTW_C, OTW_REF),
                    "latency": "host wall time from 'frame batch resident in HBM' to 'status/points of all streams visible on the host', one launch per frame"},
         "otw": o, "livenote_v2": res["livenote_v2"], "e2e": o.get("e2e"), "gpu_launches": o["gpu_launches"],
-        "cpu_baseline": cpu,
+        "roofline": otw_roof, "cpu_baseline": cpu,
     }
 
 
