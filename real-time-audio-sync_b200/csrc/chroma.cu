@@ -292,6 +292,9 @@ struct ChromaFastTables {
 constexpr int kFastStrideA = 129;   // odd row strides: 64-bit accesses whose lanes run along k1 are conflict free
 constexpr int kFastStrideB = 129;
 
+// BPT = bins per thread of the sparse filterbank when known at compile time (17 for the standard
+// librosa filterbank at sr 22050 / n_fft 4096), 0 = read it from the tables
+template <int BPT>
 __global__ void __launch_bounds__(kThreads, 4) chroma_fast_kernel(const ChromaFastTables tb, const ChromaBatch bt)
 {
     using C = Cx<float>;
@@ -452,12 +455,24 @@ __global__ void __launch_bounds__(kThreads, 4) chroma_fast_kernel(const ChromaFa
         float acc[kWin];
 #pragma unroll
         for (int w = 0; w < kWin; w++) acc[w] = 0.f;
-#pragma unroll 4
-        for (int i = 0; i < tb.bpt; i++) {
-            const float p = sP[__ldg(tb.paddr + i * kThreads + t)];
-            const float *wp = tb.wsp + (size_t)i * kWin * kThreads + t;
+        if (BPT > 0) {
+            // slot count known at compile time: every table access is base + immediate offset
+            const uint16_t *pa = tb.paddr + t;
+            const float *wp = tb.wsp + t;
 #pragma unroll
-            for (int w = 0; w < kWin; w++) acc[w] = fmaf(__ldg(wp + w * kThreads), p, acc[w]);
+            for (int i = 0; i < BPT; i++) {
+                const float p = sP[__ldg(pa + i * kThreads)];
+#pragma unroll
+                for (int w = 0; w < kWin; w++) acc[w] = fmaf(__ldg(wp + (i * kWin + w) * kThreads), p, acc[w]);
+            }
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < tb.bpt; i++) {
+                const float p = sP[__ldg(tb.paddr + i * kThreads + t)];
+                const float *wp = tb.wsp + (size_t)i * kWin * kThreads + t;
+#pragma unroll
+                for (int w = 0; w < kWin; w++) acc[w] = fmaf(__ldg(wp + w * kThreads), p, acc[w]);
+            }
         }
         float dacc = 0.f;
         if (t >= kThreads - kChroma) {          // 12 threads: the wide low bins with all 12 weights
@@ -743,12 +758,13 @@ extern "C" int afs_chroma_batch(afs_chroma_plan *pl, const float *d_audio, const
     if (compute_dtype == AFS_F32 && pl->fast_ok) {
         ChromaFastTables ft{pl->f_hann, reinterpret_cast<const float2 *>(pl->f_tw2048), reinterpret_cast<const float2 *>(pl->f_tw4096),
                             reinterpret_cast<const float2 *>(pl->f_tw1), pl->f_wsp, pl->u_paddr, pl->i_cls, pl->f_wdense, pl->u_kdense, pl->bpt, pl->nd};
+        auto kern = pl->bpt == 17 ? chroma_fast_kernel<17> : chroma_fast_kernel<0>;
         int occ = 0;
-        AFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chroma_fast_kernel, kThreads, 0));
+        AFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 0));
         if (occ < 1) return afs::fail(AFS_ERR_CUDA, "chroma fast kernel does not fit on an SM");
         int64_t blocks = (int64_t)afs::sm_count() * occ;
         if (blocks > bt.total_frames) blocks = bt.total_frames;
-        chroma_fast_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(ft, bt);
+        kern<<<(unsigned)blocks, kThreads, 0, st>>>(ft, bt);
         afs::count_launch();
         AFS_CUDA(cudaGetLastError());
         return AFS_OK;
