@@ -633,9 +633,8 @@ def bench_otw(ctx):
     for kind in ("otw", "livenote_v2"):
         b = batch.OtwBatch(ref, OTW_C, 3, kind=kind)
         st, npts, pts = b._outputs(1)
-        h_st = torch.empty_like(st, device="cpu").pin_memory()
-        h_np = torch.empty_like(npts, device="cpu").pin_memory()
-        h_pts = torch.empty_like(pts, device="cpu").pin_memory()
+        d_flat = b.outputs_flat(1)                      # status | npoints | points: one buffer, one D2H copy per step
+        h_flat = torch.empty_like(d_flat, device="cpu").pin_memory()
         h_frames = frames.cpu().pin_memory() if kind == "otw" else None
         warm = OTW_C + 100
         n_meas = min(2000, OTW_LIVE - warm - 100) if args.otw_steps <= 0 else args.otw_steps
@@ -650,9 +649,7 @@ def bench_otw(ctx):
             e0.record()
             b.step_device(fr)
             e1.record()
-            h_st.copy_(st, non_blocking=True)
-            h_np.copy_(npts, non_blocking=True)
-            h_pts.copy_(pts, non_blocking=True)
+            h_flat.copy_(d_flat, non_blocking=True)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if k >= warm:
@@ -669,9 +666,7 @@ def bench_otw(ctx):
                 t0 = time.perf_counter()
                 d_fr.copy_(h_frames[k], non_blocking=True)
                 b.step_device(d_fr)
-                h_st.copy_(st, non_blocking=True)
-                h_np.copy_(npts, non_blocking=True)
-                h_pts.copy_(pts, non_blocking=True)
+                h_flat.copy_(d_flat, non_blocking=True)
                 torch.cuda.synchronize()
                 if k >= warm:
                     lat_e2e.append((time.perf_counter() - t0) * 1e3)
@@ -685,7 +680,7 @@ def bench_otw(ctx):
         if lat_e2e:
             le = np.array(lat_e2e)
             res[kind]["e2e"] = {"value": max_over_ranks(float(np.percentile(le, 99))), "unit": "ms p99 per frame", "p50_ms": float(np.percentile(le, 50)),
-                                "h2d_bytes_per_step": int(S * 12 * 8), "d2h_bytes_per_step": int(h_st.numel() * 4 + h_np.numel() * 4 + h_pts.numel() * 4),
+                                "h2d_bytes_per_step": int(S * 12 * 8), "d2h_bytes_per_step": int(h_flat.numel() * 4),
                                 "steps": int(len(le))}
         b.close()
     if rank != 0:

@@ -68,6 +68,7 @@ class OtwBatch(object):
         nat.check(nat.lib().afs_otw_path_layout(self._h, -1, C.byref(off), C.byref(cap)))
         self.path_total = int(cap.value)
         self._out = {}
+        self._flat = {}
 
     def reset(self):
         nat.check(nat.lib().afs_otw_reset(self._h, nat.ptr(self.state), nat.stream_ptr()))
@@ -89,12 +90,22 @@ class OtwBatch(object):
 
     def _outputs(self, n_frames):
         if n_frames not in self._out:
+            # status | npoints | points are views of ONE buffer, so a host that wants all three needs a
+            # single device-to-host copy per step (`outputs_flat`)
+            k = n_frames * self.n
+            flat = torch.empty(k * (2 + 2 * self.pts), dtype=torch.int32, device=self.device)
             self._out[n_frames] = (
-                torch.empty((n_frames, self.n), dtype=torch.int32, device=self.device),
-                torch.empty((n_frames, self.n), dtype=torch.int32, device=self.device),
-                torch.empty((n_frames, self.n, self.pts, 2), dtype=torch.int32, device=self.device),
+                flat[:k].view(n_frames, self.n),
+                flat[k : 2 * k].view(n_frames, self.n),
+                flat[2 * k :].view(n_frames, self.n, self.pts, 2),
             )
+            self._flat[n_frames] = flat
         return self._out[n_frames]
+
+    def outputs_flat(self, n_frames=1):
+        """The buffer behind (status, npoints, points) of `step_device` for this n_frames."""
+        self._outputs(n_frames)
+        return self._flat[n_frames]
 
     def step_device(self, d_frames, active=None, want_points=True):
         """d_frames: device tensor (n_frames, n, 12) or (n, 12) float64.  Asynchronous.
