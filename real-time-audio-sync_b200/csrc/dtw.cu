@@ -57,7 +57,7 @@ struct DtwPair {
     int32_t M, N;
     int32_t nbands, gpad;   // gpad = nbands * 32 row groups
     int32_t nsteps;         // roundup32(N + 31)
-    int32_t prog_off;       // first progress counter of this pair
+    int32_t band0;          // index of this pair's first band in the flat band numbering (diagnostics)
     int32_t path_cap;       // M + N
     int32_t nchunks;        // ceil(N / 32)
 };
@@ -604,7 +604,7 @@ struct afs_dtw_plan {
     std::vector<DtwItem> items;
     DtwPair *d_pairs = nullptr;
     DtwItem *d_items = nullptr;
-    size_t dir_bytes = 0, brow_bytes = 0, bt_bytes = 0, prog_bytes = 0;
+    size_t dir_bytes = 0, brow_bytes = 0, bt_bytes = 0, ticket_bytes = 0;
     uint32_t epoch = 0;
     const void *last_ws = nullptr;      // workspace whose hand-off area has been cleared once
     int64_t total_path = 0;
@@ -648,7 +648,7 @@ int afs_dtw_plan_create(afs_dtw_plan **out, int n_pairs, const int64_t *h_len_a,
         q.brow_off = brow_elems;
         q.bt_off = bt_elems;
         q.path_off = path_pairs;
-        q.prog_off = prog;
+        q.band0 = prog;
         q.path_cap = (int32_t)(M + N);
         dir_units += (int64_t)(q.nsteps / 16) * q.gpad;
         brow_elems += 2 * (int64_t)q.nsteps;
@@ -667,7 +667,7 @@ int afs_dtw_plan_create(afs_dtw_plan **out, int n_pairs, const int64_t *h_len_a,
     pl->dir_bytes = afs::align_up((size_t)dir_units * 16, 256);
     pl->brow_bytes = afs::align_up((size_t)brow_elems * sizeof(uint4), 256);
     pl->bt_bytes = afs::align_up((size_t)bt_elems * esz, 256);
-    pl->prog_bytes = 256;      // the band ticket
+    pl->ticket_bytes = 256;    // the band ticket (one int)
     cudaError_t e = cudaMalloc(&pl->d_pairs, sizeof(DtwPair) * n_pairs);
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_items, sizeof(DtwItem) * pl->items.size());
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_pairs, pl->pairs.data(), sizeof(DtwPair) * n_pairs, cudaMemcpyHostToDevice);
@@ -694,7 +694,7 @@ int afs_dtw_plan_destroy(afs_dtw_plan *pl)
 int afs_dtw_plan_workspace_bytes(const afs_dtw_plan *pl, size_t *bytes)
 {
     if (!pl || !bytes) return afs::fail(AFS_ERR_INVALID, "afs_dtw_plan_workspace_bytes: null argument");
-    *bytes = pl->dir_bytes + pl->brow_bytes + pl->bt_bytes + pl->prog_bytes;
+    *bytes = pl->dir_bytes + pl->brow_bytes + pl->bt_bytes + pl->ticket_bytes;
     return AFS_OK;
 }
 
@@ -743,7 +743,7 @@ static int launch_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b,
     args.rightb = rightb;
     args.in_flag = in_flag;
     args.out_flag = out_flag;
-    AFS_CUDA(cudaMemsetAsync(args.ticket, 0, pl->prog_bytes, st));
+    AFS_CUDA(cudaMemsetAsync(args.ticket, 0, pl->ticket_bytes, st));
     {
         const int threads = 128;
         dim3 grid((pl->max_cols_pad + threads - 1) / threads, pl->n_pairs);
