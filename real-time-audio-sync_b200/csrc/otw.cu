@@ -11,16 +11,18 @@
 // or column j, rows [t-c, t], so the device state per stream is
 //   Rw : ring of c+1 doubles = acc_cost[t, j-c .. j]   (slot = col mod (c+1))
 //   Cl : ring of c+1 doubles = acc_cost[t-c .. t, j]   (slot = row mod (c+1))
-//   LH : ring of c+1 live frames (12 doubles each)     (slot = row mod (c+1))
+//   LH : ring of c+1 live frames, feature-major [12][c+1] (slot = row mod (c+1))
 // plus the scalars t, j, previous, run_count, direction.  Cells the reference never
 // evaluated read as its fill value (1e10 for OTW, +inf for LiveNote); options that
 // fall outside the matrix (x == 0 or y == 0) are excluded, i.e. +inf here.
 //
-// One warp advances one stream.  A row (or column) sweep of <= c cells is a serial
-// chain through acc[x, y-1] (resp. acc[x-1, y]); to stay bit-exact with the float64
-// reference the chain is NOT re-associated: the 32 lanes compute each cell's cost and
-// the two chain-independent candidates in parallel into shared memory, then lane 0
-// runs  v = min(v + cost_k, m_k)  sequentially, then all lanes write the line back.
+// One warp advances one stream; a CTA advances a group of up to 7 streams in lock-step
+// rounds (see otw_step_kernel).  A row (or column) sweep of <= c cells is a serial chain
+// through acc[x, y-1] (resp. acc[x-1, y]); to stay bit-exact with the float64 reference
+// the chain is NOT re-associated: the 32 lanes of the stream's warp compute each cell's
+// cost and the two chain-independent candidates in parallel into shared memory, then ONE
+// warp runs  v = min(v + cost_k, m_k)  for all streams of the group at once (one stream
+// per lane), then every warp writes its line back.
 #include <math_constants.h>
 
 #include <vector>
@@ -30,7 +32,6 @@
 namespace {
 
 constexpr int kF = 12;
-constexpr int kOtwWarps = 4;
 enum { DIR_BOTH = 0, DIR_ROW = 1, DIR_COL = 2 };
 
 struct OtwStream {
@@ -54,6 +55,7 @@ struct OtwArgs {
     int32_t *tj;          // (n,2) mirror of (t, j) for the host
     int32_t *path_len;    // (n) mirror
     int n_streams, kind, c, max_run, metric, rs, cpad, pts;
+    int group, cstride;   // streams per CTA; doubles of chain scratch per stream (2*cpad + 2: bank-skewed)
     double fill;
     // per launch
     const double *frames;
@@ -98,31 +100,59 @@ __device__ __forceinline__ double cell_cost(int metric, const double *x, const d
     return metric == 0 ? cost_cosine(x, y) : cost_euclid(x, y);
 }
 
-// One sweep: evaluates cells k = k1 .. hi of the new line.
-//   ROW sweep (is_row): new row t over ref columns k; `fixed` = live frame, sequence = ref columns.
-//   COL sweep         : new column j over live rows k; `fixed` = ref column, sequence = live history.
-// `ring` holds the previous line (same index space as k); it is overwritten with the new line.
-// Returns the value of the last cell (k = hi) in every lane.
-__device__ __forceinline__ double otw_sweep(const OtwArgs &a, const bool is_row, const int k1, const int hi, const double *fixed,
-                            const double *ref, const int N, const double *lh, double *ring, double *sc, double *sm,
-                            const int lane)
+// ---------------------------------------------------------------------------------------------------
+// A CTA advances a GROUP of up to 7 streams (one warp each) in lock-step rounds.  Round 0 is the row
+// sweep of the frame, every further round one trip of the reference's column loop (otw_eran.py:64-85).
+// In each round every warp does the PARALLEL part of its stream's sweep (costs + the two
+// chain-independent candidates into shared memory), then warp 0 runs ALL the group's serial chains
+//   v = min(v + cost_k, m_k)
+// at once, one stream per lane, then every warp writes its line back and takes its own decisions.
+// (With one warp per stream doing its own chain, 54 % of all warp-instructions ran with one active lane.)
+constexpr int kOtwMaxGroup = 7;        // 7 warps x 4 CTAs/SM = 28 streams per SM: 4096 streams fit one wave on 148 SMs
+
+// Parallel part of one sweep over cells k = k1 .. hi of the new line.
+//   ROW sweep: new row t over ref columns k  (`fix` = live frame, sequence = ref columns)
+//   COL sweep: new column j over live rows k (`fix` = ref column,  sequence = live history)
+// `fix` points to shared memory (12 doubles).  `ring` holds the previous line in the same index space.
+__device__ __forceinline__ void sweep_parallel(const OtwArgs &a, const bool is_row, const int k1, const int hi, const double *fix,
+                                               const double *ref, const int N, const double *lh, const double *ring, double *sc,
+                                               double *sm, const int lane)
 {
     const int n = hi - k1 + 1;
     const int rs = a.rs;
     const int base_slot = k1 % rs;
+    // Software pipelining through L2 (registers are too scarce to keep several iterations' loads in
+    // flight): lanes 0..23 prefetch, for each of the 12 feature rows, the two 128-byte lines that the
+    // iteration kPf steps ahead will read.  pf_row = feature, pf_half = which line.
+    constexpr int kPf = 4;
+    const int pf_row = lane % kF, pf_half = lane / kF;
+    auto prefetch_iter = [&](int first_cell) {         // first_cell: index (k) of the iteration's lane 0
+        if (lane < 2 * kF) {
+            const int kk = first_cell + 16 * pf_half;
+            if (kk <= hi) {
+                const double *p = is_row ? ref + (int64_t)pf_row * N + kk : lh + (int64_t)pf_row * rs + (kk % rs);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
+        }
+    };
+#pragma unroll
+    for (int q = 0; q < kPf; q++) prefetch_iter(k1 + 32 * q);
     for (int idx = lane; idx < n; idx += 32) {
         const int k = k1 + idx;
+        prefetch_iter(k - lane + 32 * kPf);
         double seq[kF];
         if (is_row) {
 #pragma unroll
             for (int f = 0; f < kF; f++) seq[f] = __ldg(ref + (int64_t)f * N + k);
         } else {
-            const double *p = lh + (int64_t)(k % rs) * kF;
+            // live history is feature-major [12][rs] like the reference: consecutive lanes (consecutive rows k)
+            // read consecutive doubles -> every sector is used in full
+            const double *p = lh + (k % rs);
 #pragma unroll
-            for (int f = 0; f < kF; f++) seq[f] = p[f];
+            for (int f = 0; f < kF; f++) seq[f] = p[(int64_t)f * rs];
         }
         // live is always the first np.dot operand (otw_eran.py:220)
-        const double cst = is_row ? cell_cost(a.metric, fixed, seq) : cell_cost(a.metric, seq, fixed);
+        const double cst = is_row ? cell_cost(a.metric, fix, seq) : cell_cost(a.metric, seq, fix);
         int slot = base_slot + idx;
         if (slot >= rs) slot -= rs;
         const int slot1 = (slot == 0) ? rs - 1 : slot - 1;
@@ -133,28 +163,20 @@ __device__ __forceinline__ double otw_sweep(const OtwArgs &a, const bool is_row,
         sc[idx] = cst;
         sm[idx] = (o2 < o1) ? o2 : o1;
     }
-    __syncwarp();
-    if (lane == 0) {
-        // neighbour inside the new line before its first evaluated cell: outside the matrix
-        // (excluded) when k1 == 0, otherwise a never-evaluated cell (reads the fill value)
-        double v = (k1 == 0) ? CUDART_INF : a.fill;
-        int idx = 0;
-        for (; idx + 4 <= n; idx += 4) {
-            const double c0 = sc[idx], c1 = sc[idx + 1], c2 = sc[idx + 2], c3 = sc[idx + 3];
-            const double m0 = sm[idx], m1 = sm[idx + 1], m2 = sm[idx + 2], m3 = sm[idx + 3];
-            double x;
-            x = __dadd_rn(v, c0); v = (x < m0) ? x : m0; sc[idx] = v;
-            x = __dadd_rn(v, c1); v = (x < m1) ? x : m1; sc[idx + 1] = v;
-            x = __dadd_rn(v, c2); v = (x < m2) ? x : m2; sc[idx + 2] = v;
-            x = __dadd_rn(v, c3); v = (x < m3) ? x : m3; sc[idx + 3] = v;
-        }
-        for (; idx < n; idx++) {
-            const double x = __dadd_rn(v, sc[idx]);
-            v = (x < sm[idx]) ? x : sm[idx];
-            sc[idx] = v;
-        }
+    // neutral cells up to a multiple of four (the chain is unrolled by four): v + 0 == v, min(v, +inf) == v
+    const int n4 = (n + 3) & ~3;
+    if (lane < n4 - n) {
+        sc[n + lane] = 0.0;
+        sm[n + lane] = CUDART_INF;
     }
-    __syncwarp();
+}
+
+// Write the finished line back (sc now holds the accumulated costs) and return the last cell's value.
+__device__ __forceinline__ double sweep_finish(const OtwArgs &a, const int k1, const int hi, double *ring, const double *sc, const int lane)
+{
+    const int n = hi - k1 + 1;
+    const int rs = a.rs;
+    const int base_slot = k1 % rs;
     for (int idx = lane; idx < n; idx += 32) {
         int slot = base_slot + idx;
         if (slot >= rs) slot -= rs;
@@ -166,6 +188,35 @@ __device__ __forceinline__ double otw_sweep(const OtwArgs &a, const bool is_row,
     return last;
 }
 
+// The serial chains of the whole group, one stream per lane (executed by warp 0).
+// To stay bit-exact with the float64 reference the chain is NOT re-associated.
+__device__ __forceinline__ void chain_exec(double *scratch, const int cstride, const int cpad, const int *s_n, const double *s_v0,
+                                           const int G, const int lane)
+{
+    const int n = (lane < G) ? s_n[lane] : 0;
+    const int n4 = (n + 3) & ~3;
+    int nmax = n4;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, off));
+    double v = (lane < G) ? s_v0[lane] : 0.0;
+    double *c = scratch + (size_t)(lane < G ? lane : 0) * cstride;
+    const double *m = c + cpad;
+    for (int idx = 0; idx < nmax; idx += 4) {
+        if (idx < n4) {
+            const double2 c01 = *reinterpret_cast<const double2 *>(c + idx), c23 = *reinterpret_cast<const double2 *>(c + idx + 2);
+            const double2 m01 = *reinterpret_cast<const double2 *>(m + idx), m23 = *reinterpret_cast<const double2 *>(m + idx + 2);
+            double2 r01, r23;
+            double x;
+            x = __dadd_rn(v, c01.x); v = (x < m01.x) ? x : m01.x; r01.x = v;
+            x = __dadd_rn(v, c01.y); v = (x < m01.y) ? x : m01.y; r01.y = v;
+            x = __dadd_rn(v, c23.x); v = (x < m23.x) ? x : m23.x; r23.x = v;
+            x = __dadd_rn(v, c23.y); v = (x < m23.y) ? x : m23.y; r23.y = v;
+            *reinterpret_cast<double2 *>(c + idx) = r01;
+            *reinterpret_cast<double2 *>(c + idx + 2) = r23;
+        }
+    }
+}
+
 // first-minimum argmin of ring over indices [k1, hi] (np.argmin, otw_eran.py:197,204)
 __device__ __forceinline__ void otw_argmin(const double *ring, const int rs, const int k1, const int hi, const int lane, double &bv,
                            int &bk)
@@ -173,9 +224,14 @@ __device__ __forceinline__ void otw_argmin(const double *ring, const int rs, con
     double v = CUDART_INF;
     int kk = 0x7fffffff;
     bool have = false;
-    for (int k = k1 + lane; k <= hi; k += 32) {
-        const double x = ring[k % rs];
-        if (!have || x < v) { v = x; kk = k; have = true; }
+    // four independent loads in flight per trip (the rings are read from L2), compared in ascending k
+    for (int k = k1 + lane; k <= hi; k += 128) {
+        double x[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) x[q] = (k + 32 * q <= hi) ? ring[(k + 32 * q) % rs] : CUDART_INF;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (k + 32 * q <= hi && (!have || x[q] < v)) { v = x[q]; kk = k + 32 * q; have = true; }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -189,15 +245,19 @@ __device__ __forceinline__ void otw_argmin(const double *ring, const int rs, con
     bk = kk;
 }
 
-__global__ void __launch_bounds__(kOtwWarps * 32) otw_step_kernel(const OtwArgs a)
+__global__ void __launch_bounds__(kOtwMaxGroup * 32, 4) otw_step_kernel(const OtwArgs a)
 {
-    extern __shared__ double s_scratch[];
+    extern __shared__ __align__(16) double s_scratch[];      // [G][cstride] chain scratch, then [G][12] fixed vectors
+    __shared__ int s_n[8];
+    __shared__ double s_v0[8];
+    const int G = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
-    const int s = blockIdx.x * kOtwWarps + w;
-    if (s >= a.n_streams) return;
-    double *sc = s_scratch + (size_t)w * 2 * a.cpad;
+    const bool valid = blockIdx.x * G + w < a.n_streams;
+    const int s = valid ? blockIdx.x * G + w : 0;
+    double *sc = s_scratch + (size_t)w * a.cstride;
     double *sm = sc + a.cpad;
+    double *fix = s_scratch + (size_t)G * a.cstride + w * kF;
 
     const OtwStream sd = a.streams[s];
     const int N = sd.N;
@@ -213,22 +273,22 @@ __global__ void __launch_bounds__(kOtwWarps * 32) otw_step_kernel(const OtwArgs 
     for (int f = 0; f < a.n_frames; f++) {
         const int64_t oidx = (int64_t)f * a.n_streams + s;
         int status = AFS_STEP_NONE, npts = 0;
-        const bool on = (a.active == nullptr) || (a.active[s] != 0);
+        const bool on = valid && ((a.active == nullptr) || (a.active[s] != 0));
+        // ---------------- round 0: the row sweep ----------------
+        bool do_row = false;
         if (on && S.status == AFS_STEP_STOP) {
             status = AFS_STEP_STOP;            // the reference object is finished; stay finished
         } else if (on) {
-            double fr[kF];
-            const double *fp = a.frames + oidx * kF;
-#pragma unroll
-            for (int k = 0; k < kF; k++) fr[k] = __ldg(fp + k);
+            if (lane < kF) fix[lane] = __ldg(a.frames + oidx * kF + lane);
+            __syncwarp();
             if (S.first) {
                 // otw_eran.py:41-45: store column 0 and evaluate (0,0); no path point
                 S.first = 0;
-                if (lane < kF) lh[lane] = fr[lane];
+                if (lane < kF) lh[(int64_t)lane * rs] = fix[lane];
                 double r0[kF];
 #pragma unroll
                 for (int k = 0; k < kF; k++) r0[k] = __ldg(ref + (int64_t)k * N);
-                const double cst = cell_cost(a.metric, fr, r0);
+                const double cst = cell_cost(a.metric, fix, r0);
                 if (lane == 0) { rw[0] = cst; cl[0] = cst; }
                 __syncwarp();
             } else {
@@ -237,72 +297,107 @@ __global__ void __launch_bounds__(kOtwWarps * 32) otw_step_kernel(const OtwArgs 
                     status = AFS_STEP_FULL;    // otw_eran.py:53-55: live buffer exhausted, returns None forever
                                                // (t keeps counting, exactly like the reference's self.t)
                 } else {
-                    if (lane < kF) lh[(int64_t)(S.t % rs) * kF + lane] = fr[lane];
+                    if (lane < kF) lh[(int64_t)lane * rs + (S.t % rs)] = fix[lane];
                     __syncwarp();
-                    // ROW: eval(t, k) for k in [max(0, j-c+1), j]   otw_eran.py:58-62
-                    {
-                        const int k1 = max(0, S.j - c + 1);
-                        const double last = otw_sweep(a, true, k1, S.j, fr, ref, N, lh, rw, sc, sm, lane);
-                        if (lane == 0) cl[S.t % rs] = last;        // acc[t, j] joins column j
-                        __syncwarp();
-                    }
-                    for (;;) {
-                        if (S.direction != DIR_ROW) {
-                            S.j += 1;
-                            if (S.j >= N) { status = AFS_STEP_STOP; S.status = AFS_STEP_STOP; break; }   // otw_eran.py:69-71
-                            double rc[kF];
-#pragma unroll
-                            for (int k = 0; k < kF; k++) rc[k] = __ldg(ref + (int64_t)k * N + S.j);
-                            // COLUMN: eval(k, j) for k in [max(0, t-c+1), t]   otw_eran.py:73-77
-                            const int k1 = max(0, S.t - c + 1);
-                            const double last = otw_sweep(a, false, k1, S.t, rc, ref, N, lh, cl, sc, sm, lane);
-                            if (lane == 0) rw[S.j % rs] = last;    // acc[t, j] joins row t
-                            __syncwarp();
-                        }
-                        // best_point: otw_eran.py:192-211
-                        double cj, ct;
-                        int bj, bt;
-                        otw_argmin(rw, rs, max(0, S.j - c + 1), S.j, lane, cj, bj);
-                        otw_argmin(cl, rs, max(0, S.t - c + 1), S.t, lane, ct, bt);
-                        int x, y;
-                        if (cj < ct) { x = S.t; y = bj; } else { x = bt; y = S.j; }
-                        // path append: always (otw_eran.py:160), forward-only for LiveNoteV2 (livenote_v2.py:198-199)
-                        bool app = true;
-                        if (a.kind == AFS_LIVENOTE_V2 && S.path_len > 0) app = (x > S.last_x) && (y >= S.last_y);
-                        if (app) {
-                            if (lane == 0) {
-                                if (S.path_len < sd.path_cap) path[S.path_len] = make_int2(x, y);
-                                if (a.out_points && npts < a.pts) {
-                                    a.out_points[(oidx * a.pts + npts) * 2 + 0] = x;
-                                    a.out_points[(oidx * a.pts + npts) * 2 + 1] = y;
-                                }
-                            }
-                            S.path_len += 1;
-                            S.last_x = x;
-                            S.last_y = y;
-                            npts += 1;
-                        }
-                        // set_direction: otw_eran.py:162-188
-                        int nd;
-                        if (S.t < c) nd = DIR_BOTH;
-                        else if (S.run_count >= a.max_run) nd = (S.previous == DIR_ROW) ? DIR_COL : DIR_ROW;
-                        else if (x < S.t) nd = DIR_COL;
-                        else if (y < S.j) nd = DIR_ROW;
-                        else nd = DIR_BOTH;
-                        if (nd != DIR_BOTH && nd == S.previous) S.run_count += 1; else S.run_count = 1;
-                        if (nd != DIR_BOTH) S.previous = nd;
-                        S.direction = nd;
-                        if (nd != DIR_COL) break;
-                    }
+                    do_row = true;
                 }
             }
         }
+        int k1 = 0;
+        if (do_row) {
+            // ROW: eval(t, k) for k in [max(0, j-c+1), j]   otw_eran.py:58-62
+            k1 = max(0, S.j - c + 1);
+            sweep_parallel(a, true, k1, S.j, fix, ref, N, lh, rw, sc, sm, lane);
+        }
         if (lane == 0) {
+            s_n[w] = do_row ? S.j - k1 + 1 : 0;
+            // neighbour before the first evaluated cell: outside the matrix (excluded) when k1 == 0, otherwise a
+            // never-evaluated cell of the new line (reads the fill value)
+            s_v0[w] = (k1 == 0) ? CUDART_INF : a.fill;
+        }
+        __syncthreads();
+        if (w == 0) chain_exec(s_scratch, a.cstride, a.cpad, s_n, s_v0, G, lane);
+        __syncthreads();
+        bool looping = false;
+        if (do_row) {
+            const double last = sweep_finish(a, k1, S.j, rw, sc, lane);
+            if (lane == 0) cl[S.t % rs] = last;        // acc[t, j] joins column j
+            __syncwarp();
+            looping = true;
+        }
+        // ---------------- further rounds: the column loop, otw_eran.py:64-85 ----------------
+        while (__syncthreads_or(looping ? 1 : 0)) {
+            bool do_col = false;
+            if (looping && S.direction != DIR_ROW) {
+                S.j += 1;
+                if (S.j >= N) {                                  // otw_eran.py:69-71
+                    status = AFS_STEP_STOP;
+                    S.status = AFS_STEP_STOP;
+                    looping = false;
+                } else {
+                    if (lane < kF) fix[lane] = __ldg(ref + (int64_t)lane * N + S.j);
+                    __syncwarp();
+                    // COLUMN: eval(k, j) for k in [max(0, t-c+1), t]   otw_eran.py:73-77
+                    k1 = max(0, S.t - c + 1);
+                    sweep_parallel(a, false, k1, S.t, fix, ref, N, lh, cl, sc, sm, lane);
+                    do_col = true;
+                }
+            }
+            if (lane == 0) {
+                s_n[w] = do_col ? S.t - k1 + 1 : 0;
+                s_v0[w] = (k1 == 0) ? CUDART_INF : a.fill;
+            }
+            __syncthreads();
+            if (w == 0) chain_exec(s_scratch, a.cstride, a.cpad, s_n, s_v0, G, lane);
+            __syncthreads();
+            if (looping) {
+                if (do_col) {
+                    const double last = sweep_finish(a, k1, S.t, cl, sc, lane);
+                    if (lane == 0) rw[S.j % rs] = last;    // acc[t, j] joins row t
+                    __syncwarp();
+                }
+                // best_point: otw_eran.py:192-211
+                double cj, ct;
+                int bj, bt;
+                otw_argmin(rw, rs, max(0, S.j - c + 1), S.j, lane, cj, bj);
+                otw_argmin(cl, rs, max(0, S.t - c + 1), S.t, lane, ct, bt);
+                int x, y;
+                if (cj < ct) { x = S.t; y = bj; } else { x = bt; y = S.j; }
+                // path append: always (otw_eran.py:160), forward-only for LiveNoteV2 (livenote_v2.py:198-199)
+                bool app = true;
+                if (a.kind == AFS_LIVENOTE_V2 && S.path_len > 0) app = (x > S.last_x) && (y >= S.last_y);
+                if (app) {
+                    if (lane == 0) {
+                        if (S.path_len < sd.path_cap) path[S.path_len] = make_int2(x, y);
+                        if (a.out_points && npts < a.pts) {
+                            a.out_points[(oidx * a.pts + npts) * 2 + 0] = x;
+                            a.out_points[(oidx * a.pts + npts) * 2 + 1] = y;
+                        }
+                    }
+                    S.path_len += 1;
+                    S.last_x = x;
+                    S.last_y = y;
+                    npts += 1;
+                }
+                // set_direction: otw_eran.py:162-188
+                int nd;
+                if (S.t < c) nd = DIR_BOTH;
+                else if (S.run_count >= a.max_run) nd = (S.previous == DIR_ROW) ? DIR_COL : DIR_ROW;
+                else if (x < S.t) nd = DIR_COL;
+                else if (y < S.j) nd = DIR_ROW;
+                else nd = DIR_BOTH;
+                if (nd != DIR_BOTH && nd == S.previous) S.run_count += 1; else S.run_count = 1;
+                if (nd != DIR_BOTH) S.previous = nd;
+                S.direction = nd;
+                if (nd != DIR_COL) looping = false;
+            }
+        }
+        if (valid && lane == 0) {
             if (a.out_status) a.out_status[oidx] = status;
             if (a.out_npoints) a.out_npoints[oidx] = npts;
         }
     }
-    if (lane == 0) {
+    if (valid && lane == 0) {
         a.scal[s] = S;
         a.tj[2 * s] = S.t;
         a.tj[2 * s + 1] = S.j;
@@ -373,9 +468,16 @@ int afs_otw_create(afs_otw **out, int kind, int n_streams, const double *d_ref, 
     if (kind < AFS_OTW || kind > AFS_LIVENOTE_V1) return afs::fail(AFS_ERR_INVALID, "afs_otw: bad kind %d", kind);
     if (cost_kind != AFS_COST_COSINE && cost_kind != AFS_COST_EUCLID) return afs::fail(AFS_ERR_INVALID, "afs_otw: bad cost kind");
     if (c < 1 || max_run < 1) return afs::fail(AFS_ERR_INVALID, "afs_otw: c and max_run_count must be >= 1");
-    const int cpad = (c + 31) / 32 * 32;
-    const size_t smem = (size_t)kOtwWarps * 2 * cpad * sizeof(double);
-    if (smem > 200 * 1024) return afs::fail(AFS_ERR_UNSUPPORTED, "afs_otw: c = %d needs %zu B of shared memory per block (max 200 KiB)", c, smem);
+    const int cpad = (c + 3) / 4 * 4;
+    const int cstride = 2 * cpad + 2;                                   // +2 doubles: consecutive streams start 4 banks apart
+    const size_t per_stream = (size_t)(cstride + kF) * sizeof(double);
+    // four CTAs per SM (232448 B of shared memory, 1 KB reserved per CTA) when c allows it
+    int group = (int)((232448 / 4 - 1024 - 256) / per_stream);
+    if (group > kOtwMaxGroup) group = kOtwMaxGroup;
+    if (group < 1) group = (int)((227 * 1024 - 256) / per_stream) >= 1 ? 1 : 0;
+    if (group < 1) return afs::fail(AFS_ERR_UNSUPPORTED, "afs_otw: c = %d needs %zu B of shared memory per stream (max 227 KiB)", c, per_stream);
+    if (group > n_streams) group = n_streams;
+    const size_t smem = (size_t)group * per_stream;
     afs_otw *h = new afs_otw();
     memset(&h->args, 0, sizeof(h->args));
     h->streams.resize(n_streams);
@@ -399,6 +501,8 @@ int afs_otw_create(afs_otw **out, int kind, int n_streams, const double *d_ref, 
     a.metric = cost_kind;
     a.rs = c + 1;
     a.cpad = cpad;
+    a.group = group;
+    a.cstride = cstride;
     a.pts = max_run + 2;
     a.fill = (kind == AFS_OTW) ? 1e10 : (double)INFINITY;   // otw_eran.py:27 / livenote_v2.py:22-23
     h->smem_bytes = smem;
@@ -489,8 +593,8 @@ int afs_otw_step(afs_otw *h, const double *d_frames, int n_frames, const uint8_t
     a.out_status = d_status;
     a.out_npoints = d_npoints;
     a.out_points = d_points;
-    const int blocks = (a.n_streams + kOtwWarps - 1) / kOtwWarps;
-    otw_step_kernel<<<blocks, kOtwWarps * 32, h->smem_bytes, static_cast<cudaStream_t>(stream)>>>(a);
+    const int blocks = (a.n_streams + a.group - 1) / a.group;
+    otw_step_kernel<<<blocks, a.group * 32, h->smem_bytes, static_cast<cudaStream_t>(stream)>>>(a);
     afs::count_launch();
     AFS_CUDA(cudaGetLastError());
     return AFS_OK;
