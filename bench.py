@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--chroma-tracks", type=int, default=CHROMA_TRACKS)
     ap.add_argument("--otw-streams", type=int, default=OTW_STREAMS)
     ap.add_argument("--otw-steps", type=int, default=0)
+    ap.add_argument("--wtw-streams", type=int, default=1024)
     ap.add_argument("--striped-cols-per-gpu", type=int, default=25000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -241,6 +242,8 @@ def main():
         results["chroma"] = bench_chroma(ctx)
     if "otw" in wl:
         results["otw"] = bench_otw(ctx)
+    if "wtw" in wl or args.workloads == "all":
+        results["wtw"] = bench_wtw(ctx)
     if world > 1 and ("striped" in wl or args.workloads == "all"):
         ctx["dist"] = dist
         results["striped"] = bench_striped(ctx)
@@ -255,6 +258,38 @@ def main():
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- WTW (cfg[4]'s windowed variant)
+def bench_wtw(ctx):
+    """Windowed time warping on chroma columns, many replicas per GPU (WTW is a serial chain of windows per stream, so
+    it shards by stream only).  Two window shapes: the offline parameters of test_simple.py:168 (W = 20, h = 10) and
+    the live app's (wtw_live.py:106: W = 100, h = 50).  Whole live sequence in one launch; frames/s = live frames of
+    all streams / device time."""
+    args, rank, world, torch, g = ctx["args"], ctx["rank"], ctx["world"], ctx["torch"], ctx["g"]
+    batch = g.submodule("batch")
+    S = args.wtw_streams
+    ref, frames = synth_streams(torch, S, OTW_REF, OTW_LIVE, 4000 + rank, "cuda")
+    out = {"metric": "wtw_frames_per_s", "unit": "live frames/s", "n_gpus": world, "streams_per_gpu": S, "ref_frames": OTW_REF, "shapes": {}}
+    for W, h in ((20, 10), (100, 50)):
+        b = batch.WtwBatch(ref, W, h)
+        b.push_device(frames[:200].contiguous())
+        b.reset()
+        torch.cuda.synchronize()
+        ctx["barrier"]()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st = b.push_device(frames)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = ctx["max_over_ranks"](e0.elapsed_time(e1))
+        n_live = int(frames.shape[0])
+        lens = [len(p) for p in b.paths()[:8]]
+        out["shapes"]["W%d_h%d" % (W, h)] = {"ms": ms, "value": S * world * n_live / (ms * 1e-3), "windows_per_s": S * world * (n_live / h) / (ms * 1e-3),
+                                              "path_len_first_streams": lens}
+        b.close()
+    out["value"] = out["shapes"]["W100_h50"]["value"]
+    return out if rank == 0 else None
 
 
 # ----------------------------------------------------------------------------- striped single pair (cfg[4])
@@ -376,6 +411,27 @@ def bench_dtw(ctx):
     e2e_val = cells_rank * world / e2e_s / 1e9
     h2d = int(h_a.numel() * h_a.element_size() + h_b.numel() * h_b.element_size())
     d2h = int(h_path.numel() * 4 + h_start.numel() * 4 + h_len.numel() * 4 + h_end.numel() * 8)
+    # ---- the other arithmetic mode on the same data (kernel only): fp32 offsets against fp64 bases ----
+    other = None
+    if args.dtype == "fp64":
+        end64 = plan.acc_end.cpu().numpy().copy()
+        plan32 = dtw.DtwPlan([Ln] * P, [Ln] * P, dtype="fp32")
+        a32, b32 = d_a.to(torch.float32), d_b.to(torch.float32)
+        for _ in range(2):
+            plan32.accumulate(a32, b32)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            plan32.accumulate(a32, b32)
+        e1.record()
+        torch.cuda.synchronize()
+        ms32 = max_over_ranks(e0.elapsed_time(e1) / 3)
+        end32 = plan32.acc_end.cpu().numpy()
+        other = {"dtype": "f32 (re-based offsets, fp64 bases)", "accumulate_ms": ms32,
+                 "value": cells_rank * world / (ms32 * 1e-3) / 1e9, "unit": "GCUPS (accumulate kernel only)",
+                 "max_rel_err_acc_end_vs_f64": float(np.max(np.abs(end32 - end64) / np.abs(end64))), "tolerance": 1e-5}
+        plan32.close()
+        del a32, b32
     if rank != 0:
         return None
     peaks = load_peaks()
@@ -413,6 +469,7 @@ def bench_dtw(ctx):
                    "l2": "256 MiB flush between timed steps; per-step working set 3.2 GB direction map > 126 MB L2",
                    "step": "accumulate (K2) + backtrack (K3)", "parallelism": "pairs sharded over ranks, no collective"},
         "kernel_ms": {"accumulate": acc_ms_mean, "backtrack": float(np.mean(bt_ms))},
+        "fp32_mode": other,
         "wall_s_timed_region": t_wall,
         "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
         "gpu_launches": int(launches),
