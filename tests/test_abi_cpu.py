@@ -65,3 +65,32 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), "%s mentions the oracle" % f
+
+
+def test_host_side_filterbank_matches_oracle_restatement(entry):
+    """chroma.chroma_filterbank (product, host side, feeds afs_chroma_plan_create) vs the oracle's restatement of
+    librosa.filters.chroma and the independent port in transformers."""
+    import numpy as np
+    chroma = entry.submodule("chroma")
+    from oracle import librosa_restated as lr
+    fb = chroma.chroma_filterbank(22050, 4096)
+    assert fb.shape == (12, 2049) and np.array_equal(fb, lr.filters_chroma(22050, 4096))
+    assert chroma.fft_len == 4096 and chroma.hop_size == 2048 and chroma.fs == 22050      # chroma.py:20-22
+
+
+def test_drop_in_module_names_and_signatures(entry):
+    """The reference's import lines keep working when the package directory is on sys.path."""
+    import inspect
+    import subprocess
+    import sys
+    import os
+    pkg = entry.PKG_DIR
+    code = ("import sys; sys.path.insert(0, %r); "
+            "from chroma import wav_to_chroma, wav_to_chroma_col, wav_to_chroma_diff, create_stft, create_chroma; "
+            "from dtw import DTW; from otw_eran import OnlineTimeWarping; from livenote_v2 import LiveNoteV2; "
+            "from livenote import LiveNote; from wtw import WTW; import inspect; "
+            "print(list(inspect.signature(DTW).parameters)[:2], list(inspect.signature(OnlineTimeWarping.__init__).parameters)[:3], "
+            "list(inspect.signature(LiveNoteV2.__init__).parameters)[:5], list(inspect.signature(WTW.__init__).parameters)[:4])") % pkg
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "['seq_a', 'seq_b'] ['self', 'ref', 'params'] ['self', 'ref', 'params', 'debug_params', 'chroma_diff'] ['self', 'ref_recording', 'params', 'debug_params']" in out.stdout
