@@ -91,3 +91,21 @@ def test_chroma_diff(chroma, audio):
     c = chroma.wav_samples_to_chroma(audio["ref"], compute="fp64")
     d = chroma.chroma_to_diff(c)
     assert d.shape == (12, c.shape[1] - 1) and (d >= 0).all()
+
+
+def test_wav_to_chroma_from_a_wav_file(chroma, audio, tmp_path):
+    """chroma.wav_to_chroma(path) / wav_to_chroma_diff(path) on a PCM16 stereo WAV (the excerpt of the
+    reference's own recording): same numbers as the reference's chroma of that audio."""
+    import wave
+    aud = np.load(os.path.join(GOLD, "audio_15s.npz"))
+    path = os.path.join(str(tmp_path), "excerpt.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(2)
+        w.setframerate(22050)
+        w.writeframes(aud["ref_i16"].astype("<i2").tobytes())
+    got = chroma.wav_to_chroma(path)
+    assert got.shape == audio["ref_chroma"].shape and np.abs(got - audio["ref_chroma"]).max() < TOL_F32
+    d = chroma.wav_to_chroma_diff(path)
+    want = np.clip(np.diff(audio["ref_chroma"]), 0, np.inf)
+    assert d.shape == want.shape and np.abs(d - want).max() < 2 * TOL_F32
