@@ -212,7 +212,7 @@ __global__ void dtw_pack_b_kernel(const T *__restrict__ b, T *__restrict__ bt, c
 
 template <typename T, bool DENSE, int U>
 __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane, const int band, const DtwPair &pm,
-                                         const uint32_t ring_s, const uint32_t ubuf_s, const uint32_t obuf_s, const bool feeds_next,
+                                         const uint32_t ring_s, const uint32_t ubuf_s, T *obuf, const bool feeds_next,
                                          uint32_t &dw, const DtwArgs<T> &args, const double base)
 {
     using A = Arith<T>;
@@ -224,50 +224,55 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
     // lane 0 takes it from the band above (staged in ubuf)
     T up = __shfl_up_sync(full, L.bottom, 1);
     if (lane == 0) up = A::lds(ubuf_s + (s & 31) * (int)sizeof(T));
-    if ((unsigned)j < (unsigned)N) {
-        T c[kRows];
-        {
-            T bk[kF];
-            A::load_col(ring_s + (j & (kRingSlots * kChunkCols - 1)) * (S * (int)sizeof(T)), bk);
+    const bool act = (unsigned)j < (unsigned)N;
+    if (DENSE) {
+        if (!act) return;
+    }
+    // Batch kernels are branch-free: lanes outside [0, N) (start-up / drain of the skew) compute on whatever
+    // the ring holds and simply do not commit.  The four unrolled steps then form one basic block, so the
+    // next column's loads and dot products can be scheduled under the current column's dependent DP chain.
+    T c[kRows];
+    {
+        T bk[kF];
+        A::load_col(ring_s + (j & (kRingSlots * kChunkCols - 1)) * (S * (int)sizeof(T)), bk);
 #pragma unroll
-            for (int r = 0; r < kRows; r++) c[r] = A::mul(L.ar[r][0], bk[0]);
+        for (int r = 0; r < kRows; r++) c[r] = A::mul(L.ar[r][0], bk[0]);
 #pragma unroll
-            for (int k = 1; k < kF; k++)
+        for (int k = 1; k < kF; k++)
 #pragma unroll
-                for (int r = 0; r < kRows; r++) c[r] = A::fma(L.ar[r][k], bk[k], c[r]);
+            for (int r = 0; r < kRows; r++) c[r] = A::fma(L.ar[r][k], bk[k], c[r]);
 #pragma unroll
-            for (int r = 0; r < kRows; r++) c[r] = A::sub((T)1, c[r]);    // dtw.py:11
-        }
-        T diag = L.up_prev;
-        T upv = up;
-        uint32_t nib = 0;
+        for (int r = 0; r < kRows; r++) c[r] = A::sub((T)1, c[r]);    // dtw.py:11
+    }
+    T diag = L.up_prev;
+    T upv = up;
+    uint32_t nib = 0;
 #pragma unroll
-        for (int r = 0; r < kRows; r++) {
-            T x = A::add(L.left[r], c[r]);                  // (i, j-1)   dtw.py:35
-            T y = A::add(upv, c[r]);                        // (i-1, j)   dtw.py:36
-            T z = A::fma((T)2, c[r], diag);                 // (i-1, j-1) dtw.py:37 (2c exact)
-            const bool yx = y < x;                          // np.argmin: first minimum wins
-            T m = yx ? y : x;
-            const bool zm = z < m;
-            T v = zm ? z : m;
-            uint32_t code = zm ? 2u : (yx ? 1u : 0u);
-            nib |= code << (2 * r);
-            diag = L.left[r];
-            L.left[r] = v;
-            upv = v;
-            if (DENSE) {
-                const int64_t i = (int64_t)band * kBandRows + lane * kRows + r;
-                if (i < pm.M) {
-                    args.dense_cost[i * N + j] = c[r];
-                    args.dense_acc[i * N + j] = (T)((double)v + base);
-                }
+    for (int r = 0; r < kRows; r++) {
+        T x = A::add(L.left[r], c[r]);                  // (i, j-1)   dtw.py:35
+        T y = A::add(upv, c[r]);                        // (i-1, j)   dtw.py:36
+        T z = A::fma((T)2, c[r], diag);                 // (i-1, j-1) dtw.py:37 (2c exact)
+        const bool yx = y < x;                          // np.argmin: first minimum wins
+        T m = yx ? y : x;
+        const bool zm = z < m;
+        T v = zm ? z : m;
+        uint32_t code = zm ? 2u : (yx ? 1u : 0u);
+        nib |= code << (2 * r);
+        diag = L.left[r];
+        L.left[r] = act ? v : L.left[r];
+        upv = v;
+        if (DENSE) {
+            const int64_t i = (int64_t)band * kBandRows + lane * kRows + r;
+            if (i < pm.M) {
+                args.dense_cost[i * N + j] = c[r];
+                args.dense_acc[i * N + j] = (T)((double)v + base);
             }
         }
-        L.up_prev = up;
-        L.bottom = L.left[kRows - 1];
-        dw |= nib << (8 * U);
-        if (feeds_next && lane == 31) A::sts(obuf_s + (s & 31) * (int)sizeof(T), L.bottom);
     }
+    L.up_prev = act ? up : L.up_prev;
+    L.bottom = L.left[kRows - 1];
+    dw |= nib << (8 * U);
+    if (feeds_next && lane == 31 && act) obuf[s & 31] = L.bottom;
 }
 
 template <typename T, bool DENSE>
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
     const int w = threadIdx.x >> 5;
     WarpSmem<T> &sm = reinterpret_cast<WarpSmem<T> *>(s_dyn)[w];
     // 32-bit shared-space addresses for the per-step accesses (keeps address arithmetic out of the hot loop)
-    const uint32_t ring_s = smem_u32(sm.ring), ubuf_s = smem_u32(sm.ubuf), obuf_s = smem_u32(sm.obuf);
+    const uint32_t ring_s = smem_u32(sm.ring), ubuf_s = smem_u32(sm.ubuf);
     const unsigned full = 0xffffffffu;
 
     if (lane == 0) {
@@ -423,10 +428,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
             for (int g4 = 0; g4 < 8; g4++) {
                 const int s = s0 + g4 * 4;
                 uint32_t dw = 0;
-                dtw_step<T, DENSE, 0>(L, s + 0, lane, band, pm, ring_s, ubuf_s, obuf_s, feeds_next, dw, args, base);
-                dtw_step<T, DENSE, 1>(L, s + 1, lane, band, pm, ring_s, ubuf_s, obuf_s, feeds_next, dw, args, base);
-                dtw_step<T, DENSE, 2>(L, s + 2, lane, band, pm, ring_s, ubuf_s, obuf_s, feeds_next, dw, args, base);
-                dtw_step<T, DENSE, 3>(L, s + 3, lane, band, pm, ring_s, ubuf_s, obuf_s, feeds_next, dw, args, base);
+                dtw_step<T, DENSE, 0>(L, s + 0, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
+                dtw_step<T, DENSE, 1>(L, s + 1, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
+                dtw_step<T, DENSE, 2>(L, s + 2, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
+                dtw_step<T, DENSE, 3>(L, s + 3, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
                 d0 = d1; d1 = d2; d2 = d3; d3 = dw;
                 if ((g4 & 3) == 3) {
                     const int cbp = s >> 4;
