@@ -30,6 +30,8 @@
 // 32 x 16 B = 512 contiguous bytes every 16 steps (unit index = cbp * gpad + g).
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include <vector>
 
 #include "afs_common.cuh"
@@ -136,6 +138,7 @@ struct DtwArgs {
     double *rightb;        // [M] out: acc of this stripe's last column (may be peer-mapped memory)
     const int *in_flag;    // [nbands] raised by the left stripe when leftb rows of a band are valid (null: valid already)
     int *out_flag;         // [nbands] raised for the right stripe (may be peer-mapped; null: none)
+    unsigned long long wait_ns;   // bound on the in_flag wait
 };
 
 // Per-lane wavefront state.
@@ -148,6 +151,16 @@ struct Lane {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K4 only: longest a band waits for the stripe on its left before the launch is declared failed
+// (default; the environment variable AFS_STRIPE_WAIT_MS overrides it per launch).
+constexpr unsigned long long kStripeWaitNs = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
 {
@@ -347,8 +360,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
                 // column stripe of a longer pair (K4): column -1 of this stripe is the last column of the
                 // stripe to the left.  Wait until that stripe (another GPU, or an earlier launch) has
                 // finished this band, then take acc[i, c0-1] as `left` and acc[i-1, c0-1] as the first diag.
-                if (args.in_flag != nullptr)
-                    while (afs::ld_acquire_sys(args.in_flag + band) == 0) __nanosleep(200);
+                if (args.in_flag != nullptr) {
+                    // Bounded wait: a neighbour that never launches (crashed rank) must not hang this
+                    // GPU.  After kStripeWaitNs the launch is marked failed (ticket[1]) and acc_end is
+                    // poisoned with NaN; the host side turns that into an error on every rank.
+                    volatile int *failed = args.ticket + 1;
+                    const unsigned long long t0 = globaltimer_ns();
+                    while (afs::ld_acquire_sys(args.in_flag + band) == 0) {
+                        __nanosleep(200);
+                        if (*failed != 0) break;
+                        if (globaltimer_ns() - t0 > args.wait_ns) {
+                            *failed = 1;
+                            args.acc_end[0] = __longlong_as_double(0x7ff8000000000000ll);
+                            break;
+                        }
+                    }
+                }
 #pragma unroll
                 for (int r = 0; r < kRows; r++)
                     if (r0 + r < pm.M) L.left[r] = (T)__ldcg(args.leftb + r0 + r);
@@ -456,7 +483,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
                 T e = L.left[0];
 #pragma unroll
                 for (int r = 1; r < kRows; r++) if (rl == r) e = L.left[r];
-                args.acc_end[it.pair] = (double)e + base;
+                double ev = (double)e + base;
+                if (args.in_flag != nullptr && *(volatile int *)(args.ticket + 1) != 0)
+                    ev = __longlong_as_double(0x7ff8000000000000ll);     // a stripe wait timed out: poisoned
+                args.acc_end[it.pair] = ev;
             }
         }
         if (args.rightb != nullptr) {
@@ -748,6 +778,11 @@ static int launch_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b,
     args.rightb = rightb;
     args.in_flag = in_flag;
     args.out_flag = out_flag;
+    args.wait_ns = kStripeWaitNs;
+    if (in_flag != nullptr) {
+        const char *ms = getenv("AFS_STRIPE_WAIT_MS");
+        if (ms != nullptr && atoll(ms) > 0) args.wait_ns = (unsigned long long)atoll(ms) * 1000000ull;
+    }
     AFS_CUDA(cudaMemsetAsync(args.ticket, 0, pl->ticket_bytes, st));
     {
         const int threads = 128;

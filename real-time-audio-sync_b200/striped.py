@@ -57,6 +57,7 @@ class _Stripe(object):
 
     def accumulate(self, d_a, d_b_stripe, leftb, in_flag, rightb_ptr, out_flag_ptr):
         p = self.plan
+        p.acc_end.zero_()          # NaN afterwards == "a wait on the left stripe timed out" (see check())
         nat.check(nat.lib().afs_dtw_accumulate_stripe(
             p._h, nat.ptr(d_a), nat.ptr(d_b_stripe), nat.ptr(p.workspace), nat.ptr(p.acc_end),
             _vp(leftb), _vp(in_flag), _vp(rightb_ptr), _vp(out_flag_ptr), nat.stream_ptr()))
@@ -192,8 +193,18 @@ class StripedDtwDistributed(object):
         torch.cuda.synchronize()
         self.dist.barrier(group=self.group)
 
+    def check(self):
+        """Collective: raise AfsError on EVERY rank if any rank's stripe kernel gave up waiting for its left
+        neighbour (the kernel bounds that wait, so a crashed rank cannot hang the other GPUs)."""
+        dev = self.stripe.plan.device
+        bad = torch.isnan(self.stripe.plan.acc_end[:1]).to(torch.int32)
+        self.dist.all_reduce(bad, op=self.dist.ReduceOp.MAX, group=self.group)
+        if int(bad.cpu()[0]) != 0:
+            raise nat.AfsError("striped DTW: a stripe timed out waiting for the stripe on its left; results are invalid")
+
     def backtrack(self):
         """Returns the full path on rank 0 (None elsewhere) and acc_end on the last rank."""
+        self.check()
         dev = self.stripe.plan.device
         width = self.bounds[self.rank][1] - self.bounds[self.rank][0]
         seg = handoff_backtrack(self.rank, self.world, lambda i: self.stripe.backtrack(i, width - 1), self.M - 1,

@@ -52,3 +52,29 @@ def test_striped_two_gpus_peer_memory_handoff():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "PARITY path True acc_end True" in out.stdout, out.stdout[-2000:]
+
+
+def test_stripe_wait_is_bounded(striped, monkeypatch):
+    """A stripe whose left neighbour never raises its flags (crashed rank) must not hang the GPU: the kernel gives up
+    after AFS_STRIPE_WAIT_MS, finishes, and poisons acc_end with NaN (StripedDtwDistributed.check() raises on it)."""
+    import time
+    import torch
+    monkeypatch.setenv("AFS_STRIPE_WAIT_MS", "200")
+    rng = np.random.default_rng(5)
+    M, W = 700, 96
+    a, b = chroma_like(rng, M), chroma_like(rng, W)
+    st = striped._Stripe(M, W, 50, False)
+    leftb = torch.zeros(M, dtype=torch.float64, device="cuda")
+    in_flag = torch.zeros((M + 127) // 128, dtype=torch.int32, device="cuda")      # never raised
+    t0 = time.perf_counter()
+    st.accumulate(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), leftb, in_flag, None, None)
+    torch.cuda.synchronize()
+    waited = time.perf_counter() - t0
+    assert 0.15 < waited < 5.0
+    assert bool(torch.isnan(st.plan.acc_end[0]))
+    # the same stripe with the flags raised completes normally
+    in_flag.fill_(1)
+    st.accumulate(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), leftb, in_flag, None, None)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(st.plan.acc_end[0]))
+    st.close()
