@@ -572,37 +572,55 @@ def bench_chroma(ctx):
     h_out = torch.empty((T // slab_tracks, 12 * frames_slab), dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream()
 
-    def step_e2e():
+    def step_e2e(h_src, d_bufs):
         evs = []
         for i in range(T // slab_tracks):
             b = i & 1
             if i >= 2:
                 copy_stream.wait_event(evs[i - 2])      # slab b is free once its previous kernel + D2H are done
             with torch.cuda.stream(copy_stream):
-                d_slabs[b].copy_(h_slab, non_blocking=True)
+                d_bufs[b].copy_(h_src, non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(copy_stream)
             torch.cuda.current_stream().wait_event(ready)
-            plan.run(d_slabs[b], slab_offs, d_out=d_outs[b])
+            plan.run(d_bufs[b], slab_offs, d_out=d_outs[b])
             h_out[i].copy_(d_outs[b], non_blocking=True)
             done = torch.cuda.Event()
             done.record()
             evs.append(done)
         torch.cuda.synchronize()
 
-    e2e = None
-    if T % slab_tracks == 0:
-        step_e2e()
+    def time_e2e(h_src, d_bufs, sample_bytes, what):
+        step_e2e(h_src, d_bufs)
         barrier()
         t0 = time.perf_counter()
         e2e_steps = 2
         for _ in range(e2e_steps):
-            step_e2e()
+            step_e2e(h_src, d_bufs)
         barrier()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
-        e2e = {"value": frames * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(T * n * 4),
-               "d2h_bytes_per_step": int(12 * frames * 4), "steps": e2e_steps,
-               "note": "64 distinct pinned host tracks reused to fill all %d track slots; double-buffered slabs" % T}
+        return {"value": frames * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(T * n * sample_bytes),
+                "d2h_bytes_per_step": int(12 * frames * 4), "steps": e2e_steps,
+                "note": "%s; 64 distinct pinned host tracks reused to fill all %d track slots; double-buffered slabs" % (what, T)}
+
+    e2e = e2e_pcm = pcm_resident = None
+    if T % slab_tracks == 0:
+        e2e = time_e2e(h_slab, d_slabs, 4, "float32 samples on the host (what librosa.load returns)")
+        # the same tracks as 16-bit PCM (what the WAV files hold): half the PCIe bytes, 1/32768 applied in the kernel
+        del d_slabs
+        h_pcm = (h_slab * 32768.0).round().clamp_(-32768, 32767).to(torch.int16).pin_memory()
+        d_pcm = [torch.empty(slab_tracks * n, dtype=torch.int16, device="cuda") for _ in range(2)]
+        e2e_pcm = time_e2e(h_pcm, d_pcm, 2, "int16 PCM samples on the host (afs_chroma_batch_pcm16)")
+        plan.run(d_pcm[0], slab_offs, d_out=d_outs[0])
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(3):
+            plan.run(d_pcm[0], slab_offs, d_out=d_outs[0])
+        p1.record()
+        torch.cuda.synchronize()
+        pcm_resident = {"value": frames_slab * 3 / (p0.elapsed_time(p1) * 1e-3), "unit": "frames/s per GPU",
+                        "note": "int16 samples resident in HBM, %d tracks per launch" % slab_tracks}
     if rank != 0:
         return None
     peaks = load_peaks()
@@ -619,8 +637,8 @@ def bench_chroma(ctx):
         "data": "synthetic", "vs_baseline": None,
         "config": {"workload": "batched chroma extraction: %d synthetic 5-min 22.05 kHz tracks per GPU, n_fft=4096, hop=2048 (BASELINE cfg[1])" % T,
                    "tracks_per_gpu": T, "frames_per_step": frames, "l2": "27 GB of input per step >> 126 MB L2"},
-        "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": {"kernel": "chroma_kernel<float>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+        "e2e": e2e, "e2e_pcm16": e2e_pcm, "pcm16_resident": pcm_resident, "gpu_launches": int(launches),
+        "roofline": {"kernel": "chroma_fast_kernel<17>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": gbs / hbm_peak, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                      "bytes_per_frame": CHROMA_BYTES_PER_FRAME,
                      # ncu (profiles/ncu_raw_r1d_chroma.csv): 346.06 MB of DRAM traffic for a 41 344-frame launch

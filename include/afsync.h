@@ -165,6 +165,13 @@ int64_t afs_chroma_num_frames(const afs_chroma_plan *plan, int64_t n_samples, in
 int afs_chroma_batch(afs_chroma_plan *plan, const float *d_audio, const int64_t *h_offsets, int n_tracks,
                      int center_pad, int normalize, void *d_out, const int64_t *h_out_offsets,
                      int out_dtype, int compute_dtype, void *stream);
+/* Same, for 16-bit PCM samples as they sit in the reference's WAV files (Songs/ * / *.wav):
+ * sample = value / 32768, exactly librosa.load's int16 scaling (chroma.py:26, test_simple.py:98-99), applied
+ * on the device (folded into the window, a power of two: results are bit-identical to afs_chroma_batch on
+ * the converted samples).  Halves the host->device bytes of a track. */
+int afs_chroma_batch_pcm16(afs_chroma_plan *plan, const int16_t *d_pcm, const int64_t *h_offsets, int n_tracks,
+                           int center_pad, int normalize, void *d_out, const int64_t *h_out_offsets,
+                           int out_dtype, int compute_dtype, void *stream);
 
 /* ===================================================================== WTW
  * Replaces wtw.WTW.insert's window loop (wtw.py:100-128) with get_cost_matrix

@@ -79,10 +79,11 @@ class ChromaPlan(object):
 
     def run(self, d_audio, offsets, d_out=None, center=True, normalize=True, out_dtype=torch.float32, compute="fp32",
             out_offsets=None):
-        """K1 on the current stream.  d_audio: float32 device tensor holding all tracks;
+        """K1 on the current stream.  d_audio: float32 device tensor holding all tracks, or int16 PCM
+        (sample = value / 32768 as librosa.load scales WAV data; converted inside the kernel);
         offsets: (n_tracks+1) sample offsets.  Returns (d_out, frame_offsets): track k's chroma
         is d_out[12*frame_offsets[k] : 12*frame_offsets[k+1]].view(12, frames_k)."""
-        assert d_audio.is_cuda and d_audio.dtype == torch.float32
+        assert d_audio.is_cuda and d_audio.dtype in (torch.float32, torch.int16)
         offs = np.ascontiguousarray(offsets, dtype=np.int64)
         n = offs.shape[0] - 1
         frames = np.array([self.num_frames(offs[k + 1] - offs[k], center) for k in range(n)], dtype=np.int64)
@@ -90,7 +91,8 @@ class ChromaPlan(object):
         if d_out is None:
             d_out = torch.empty(int(12 * foffs[-1]), dtype=out_dtype, device=d_audio.device)
         oo = None if out_offsets is None else np.ascontiguousarray(out_offsets, dtype=np.int64)
-        nat.check(nat.lib().afs_chroma_batch(
+        entry = nat.lib().afs_chroma_batch_pcm16 if d_audio.dtype == torch.int16 else nat.lib().afs_chroma_batch
+        nat.check(entry(
             self._h, nat.ptr(d_audio), offs.ctypes.data_as(nat._i64p), n, 1 if center else 0, 1 if normalize else 0,
             nat.ptr(d_out), None if oo is None else oo.ctypes.data_as(nat._i64p),
             nat.AFS_F64 if d_out.dtype == torch.float64 else nat.AFS_F32,
@@ -111,13 +113,16 @@ def default_plan():
 def chroma_batch(tracks, center=True, normalize=True, compute="fp32"):
     """Many tracks in one launch: list of 1-D sample arrays -> list of (12, frames) float64 arrays."""
     plan = default_plan()
+    # int16 tracks (raw PCM, see load_wav_pcm16) travel and are staged as int16; anything else as float32
+    pcm = len(tracks) > 0 and all(np.asarray(t).dtype == np.int16 for t in tracks)
+    sdt, quantum = (np.int16, 8) if pcm else (np.float32, 4)
     # every track starts on a 16-byte boundary (TMA bulk staging of whole frames); the zero padding at a
     # track's end can at most add one frame, which is dropped below (frames are counted on the true length)
-    lens = [(len(t) + 3) // 4 * 4 for t in tracks]
+    lens = [(len(t) + quantum - 1) // quantum * quantum for t in tracks]
     offs = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
-    flat = np.zeros(int(offs[-1]), dtype=np.float32)
+    flat = np.zeros(int(offs[-1]), dtype=sdt)
     for k, t in enumerate(tracks):
-        flat[offs[k] : offs[k] + len(t)] = np.asarray(t, dtype=np.float32)
+        flat[offs[k] : offs[k] + len(t)] = np.asarray(t, dtype=sdt)
     d_audio = torch.from_numpy(flat).to(plan.device)
     outs = []
     d_out, foffs = plan.run(d_audio, offs, center=center, normalize=normalize, out_dtype=torch.float64, compute=compute)
@@ -147,11 +152,24 @@ def load_wav(path_to_wav):
     return np.ascontiguousarray(x), rate
 
 
+def load_wav_pcm16(path_to_wav):
+    """The raw int16 samples of a mono PCM16 WAV (None for other layouts) and its rate: what K1 takes directly."""
+    with wave.open(path_to_wav, "rb") as w:
+        rate, nch, width = w.getframerate(), w.getnchannels(), w.getsampwidth()
+        if width != 2 or nch != 1:
+            return None, rate
+        raw = w.readframes(w.getnframes())
+    return np.frombuffer(raw, dtype="<i2").astype(np.int16), rate
+
+
 def wav_to_chroma(path_to_wav):
-    """chroma.py:25-33."""
-    wav, wav_fs = load_wav(path_to_wav)
+    """chroma.py:25-33.  Mono PCM16 files go to the GPU as int16 (the 1/32768 scaling of librosa.load
+    happens in the kernel, bit-identically); other layouts are mixed down on the CPU first."""
+    pcm, wav_fs = load_wav_pcm16(path_to_wav)
+    if pcm is None:
+        pcm, wav_fs = load_wav(path_to_wav)
     assert(wav_fs == 22050)
-    return wav_samples_to_chroma(wav)
+    return wav_samples_to_chroma(pcm)
 
 
 def wav_to_chroma_col(wav_buf, compute="fp32"):

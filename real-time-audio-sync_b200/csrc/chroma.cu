@@ -105,7 +105,8 @@ struct ChromaTables {
 };
 
 struct ChromaBatch {
-    const float *audio;
+    const void *audio;           // float32 samples, or int16 PCM (pcm16 = 1: sample = value / 32768, librosa.load's scaling)
+    int pcm16;
     const int64_t *sample_off;   // n_tracks + 1
     const int64_t *frame_off;    // n_tracks + 1 (prefix of frames per track)
     const int64_t *out_off;      // n_tracks (frames), output placement
@@ -114,6 +115,13 @@ struct ChromaBatch {
     int hop, center_pad, normalize, out_f64;
     void *out;
 };
+
+// sample s of a track that starts at element s_begin, as librosa.load would deliver it (float32)
+__device__ __forceinline__ float load_sample(const ChromaBatch &bt, int64_t idx)
+{
+    if (bt.pcm16) return (float)__ldg(static_cast<const short *>(bt.audio) + idx) * (1.0f / 32768.0f);
+    return __ldg(static_cast<const float *>(bt.audio) + idx);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) chroma_kernel(const ChromaTables<T> tb, const ChromaBatch bt)
@@ -138,7 +146,6 @@ __global__ void __launch_bounds__(kThreads) chroma_kernel(const ChromaTables<T> 
         const int64_t n_samp = bt.sample_off[track + 1] - s_begin;
         const int64_t frames_k = bt.frame_off[track + 1] - bt.frame_off[track];
         const int64_t start = m_idx * bt.hop - (bt.center_pad ? kNfft / 2 : 0);     // chroma.py:49 left zero pad
-        const float *x = bt.audio + s_begin;
 
         // ---- pass 1: thread m = t, n1 = 0..15: z[128 n1 + m] = x[256 n1 + 2m] + i x[256 n1 + 2m + 1], windowed ----
         Cx<T> v[16];
@@ -147,11 +154,8 @@ __global__ void __launch_bounds__(kThreads) chroma_kernel(const ChromaTables<T> 
             const int n = 256 * n1 + 2 * t;
             const int64_t s = start + n;
             float2 xv = make_float2(0.f, 0.f);
-            if (s >= 0 && s + 1 < n_samp) xv = __ldg(reinterpret_cast<const float2 *>(x + s));
-            else {
-                if (s >= 0 && s < n_samp) xv.x = __ldg(x + s);
-                if (s + 1 >= 0 && s + 1 < n_samp) xv.y = __ldg(x + s + 1);
-            }
+            if (s >= 0 && s < n_samp) xv.x = load_sample(bt, s_begin + s);
+            if (s + 1 >= 0 && s + 1 < n_samp) xv.y = load_sample(bt, s_begin + s + 1);
             v[n1].x = (T)xv.x * __ldg(tb.hann + n);          // chroma.py:62 section * np.hanning
             v[n1].y = (T)xv.y * __ldg(tb.hann + n + 1);
         }
@@ -294,9 +298,13 @@ constexpr int kFastStrideB = 129;
 
 // BPT = bins per thread of the sparse filterbank when known at compile time (17 for the standard
 // librosa filterbank at sr 22050 / n_fft 4096), 0 = read it from the tables
-template <int BPT>
-__global__ void __launch_bounds__(kThreads, 4) chroma_fast_kernel(const ChromaFastTables tb, const ChromaBatch bt)
+#ifndef AFS_CHROMA_MINB
+#define AFS_CHROMA_MINB 4      // resident CTAs per SM the register budget is tuned for
+#endif
+template <int BPT, bool PCM16>
+__global__ void __launch_bounds__(kThreads, AFS_CHROMA_MINB) chroma_fast_kernel(const ChromaFastTables tb, const ChromaBatch bt)
 {
+    constexpr int kSampleBytes = PCM16 ? 2 : 4;
     using C = Cx<float>;
     __shared__ __align__(128) C sA[16 * kFastStrideA];     // staged audio of the NEXT frame (16 KB, TMA) | pass-1 output | Z natural
     __shared__ __align__(16) C sB[16 * kFastStrideB];      // pass-2 output; later power spectrum float[2052] + reduction scratch
@@ -310,7 +318,11 @@ __global__ void __launch_bounds__(kThreads, 4) chroma_fast_kernel(const ChromaFa
     // kept for k1 = 1, 2, 4, 8 only (the other eleven are products of those: 44 extra flops, 22 fewer registers)
     float2 win[16];
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) win[n1] = reinterpret_cast<const float2 *>(tb.hann)[128 * n1 + t];
+    for (int n1 = 0; n1 < 16; n1++) {
+        win[n1] = reinterpret_cast<const float2 *>(tb.hann)[128 * n1 + t];
+        // PCM16: fold librosa.load's 1/32768 into the window (a power of two: the products round identically)
+        if (PCM16) { win[n1].x *= (1.0f / 32768.0f); win[n1].y *= (1.0f / 32768.0f); }
+    }
     C w1, w2, w4, w8;
     { const float2 a = tb.tw1[0 * kThreads + t], b = tb.tw1[1 * kThreads + t], c = tb.tw1[3 * kThreads + t], d = tb.tw1[7 * kThreads + t];
       w1 = C{a.x, a.y}; w2 = C{b.x, b.y}; w4 = C{c.x, c.y}; w8 = C{d.x, d.y}; }
@@ -334,12 +346,12 @@ __global__ void __launch_bounds__(kThreads, 4) chroma_fast_kernel(const ChromaFa
         const int64_t s_begin = bt.sample_off[ld_track];
         const int64_t n_samp = bt.sample_off[ld_track + 1] - s_begin;
         const int64_t start = (f - bt.frame_off[ld_track]) * bt.hop - (bt.center_pad ? kNfft / 2 : 0);
-        const float *src = bt.audio + s_begin + start;
+        const char *src = static_cast<const char *>(bt.audio) + (s_begin + start) * kSampleBytes;
         const bool ok = (start >= 0) && (start + kNfft <= n_samp) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
         if (ok && t == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            afs::mbar_expect_tx(&sBar, kNfft * sizeof(float));
-            afs::bulk_g2s(sA, src, kNfft * sizeof(float), &sBar);
+            afs::mbar_expect_tx(&sBar, kNfft * kSampleBytes);
+            afs::bulk_g2s(sA, src, kNfft * kSampleBytes, &sBar);
         }
         return ok;
     };
@@ -357,24 +369,39 @@ __global__ void __launch_bounds__(kThreads, 4) chroma_fast_kernel(const ChromaFa
         if (staged) {
             afs::mbar_wait(&sBar, bar_phase);
             bar_phase ^= 1u;
-            const float2 *xs = reinterpret_cast<const float2 *>(sA);
+            if (PCM16) {
+                const short2 *xs = reinterpret_cast<const short2 *>(sA);
 #pragma unroll
-            for (int n1 = 0; n1 < 16; n1++) {
-                const float2 xv = xs[128 * n1 + t];
-                v[n1] = C{xv.x * win[n1].x, xv.y * win[n1].y};
+                for (int n1 = 0; n1 < 16; n1++) {
+                    const short2 xv = xs[128 * n1 + t];
+                    v[n1] = C{__fmul_rn((float)xv.x, win[n1].x), __fmul_rn((float)xv.y, win[n1].y)};
+                }
+            } else {
+                const float2 *xs = reinterpret_cast<const float2 *>(sA);
+#pragma unroll
+                for (int n1 = 0; n1 < 16; n1++) {
+                    const float2 xv = xs[128 * n1 + t];
+                    v[n1] = C{__fmul_rn(xv.x, win[n1].x), __fmul_rn(xv.y, win[n1].y)};      // no fma contraction: float and PCM16 inputs must round alike
+                }
             }
         } else {
             const int64_t s_begin = bt.sample_off[track];
             const int64_t n_samp = bt.sample_off[track + 1] - s_begin;
             const int64_t start = m_idx * bt.hop - (bt.center_pad ? kNfft / 2 : 0);
-            const float *x = bt.audio + s_begin;
 #pragma unroll
             for (int n1 = 0; n1 < 16; n1++) {
                 const int64_t s = start + 256 * n1 + 2 * t;
                 float2 xv = make_float2(0.f, 0.f);
-                if (s >= 0 && s < n_samp) xv.x = __ldg(x + s);
-                if (s + 1 >= 0 && s + 1 < n_samp) xv.y = __ldg(x + s + 1);
-                v[n1] = C{xv.x * win[n1].x, xv.y * win[n1].y};
+                if (PCM16) {
+                    const short *x = static_cast<const short *>(bt.audio) + s_begin;
+                    if (s >= 0 && s < n_samp) xv.x = (float)__ldg(x + s);
+                    if (s + 1 >= 0 && s + 1 < n_samp) xv.y = (float)__ldg(x + s + 1);
+                } else {
+                    const float *x = static_cast<const float *>(bt.audio) + s_begin;
+                    if (s >= 0 && s < n_samp) xv.x = __ldg(x + s);
+                    if (s + 1 >= 0 && s + 1 < n_samp) xv.y = __ldg(x + s + 1);
+                }
+                v[n1] = C{__fmul_rn(xv.x, win[n1].x), __fmul_rn(xv.y, win[n1].y)};      // no fma contraction: float and PCM16 inputs must round alike
             }
         }
         fft16(v);
@@ -711,9 +738,9 @@ static int launch_chroma(const ChromaTables<T> &tb, const ChromaBatch &bt, cudaS
     return AFS_OK;
 }
 
-extern "C" int afs_chroma_batch(afs_chroma_plan *pl, const float *d_audio, const int64_t *h_offsets, int n_tracks,
-                                int center_pad, int normalize, void *d_out, const int64_t *h_out_offsets, int out_dtype,
-                                int compute_dtype, void *stream)
+static int chroma_batch_impl(afs_chroma_plan *pl, const void *d_audio, int pcm16, const int64_t *h_offsets, int n_tracks,
+                             int center_pad, int normalize, void *d_out, const int64_t *h_out_offsets, int out_dtype,
+                             int compute_dtype, void *stream)
 {
     if (!pl || !d_audio || !h_offsets || !d_out || n_tracks <= 0)
         return afs::fail(AFS_ERR_INVALID, "afs_chroma_batch: null argument or n_tracks <= 0");
@@ -745,6 +772,7 @@ extern "C" int afs_chroma_batch(afs_chroma_plan *pl, const float *d_audio, const
     AFS_CUDA(cudaMemcpyAsync(pl->d_meta, meta.data(), sizeof(int64_t) * meta.size(), cudaMemcpyHostToDevice, st));
     ChromaBatch bt;
     bt.audio = d_audio;
+    bt.pcm16 = pcm16;
     bt.sample_off = pl->d_meta;
     bt.frame_off = pl->d_meta + n_tracks + 1;
     bt.out_off = pl->d_meta + 2 * (n_tracks + 1);
@@ -758,7 +786,8 @@ extern "C" int afs_chroma_batch(afs_chroma_plan *pl, const float *d_audio, const
     if (compute_dtype == AFS_F32 && pl->fast_ok) {
         ChromaFastTables ft{pl->f_hann, reinterpret_cast<const float2 *>(pl->f_tw2048), reinterpret_cast<const float2 *>(pl->f_tw4096),
                             reinterpret_cast<const float2 *>(pl->f_tw1), pl->f_wsp, pl->u_paddr, pl->i_cls, pl->f_wdense, pl->u_kdense, pl->bpt, pl->nd};
-        auto kern = pl->bpt == 17 ? chroma_fast_kernel<17> : chroma_fast_kernel<0>;
+        auto kern = pcm16 ? (pl->bpt == 17 ? chroma_fast_kernel<17, true> : chroma_fast_kernel<0, true>)
+                          : (pl->bpt == 17 ? chroma_fast_kernel<17, false> : chroma_fast_kernel<0, false>);
         int occ = 0;
         AFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 0));
         if (occ < 1) return afs::fail(AFS_ERR_CUDA, "chroma fast kernel does not fit on an SM");
@@ -775,4 +804,20 @@ extern "C" int afs_chroma_batch(afs_chroma_plan *pl, const float *d_audio, const
     }
     ChromaTables<double> tb{pl->d_hann, pl->d_tw2048, pl->d_tw4096, pl->d_fb};
     return launch_chroma<double>(tb, bt, st);
+}
+
+extern "C" int afs_chroma_batch(afs_chroma_plan *pl, const float *d_audio, const int64_t *h_offsets, int n_tracks,
+                                int center_pad, int normalize, void *d_out, const int64_t *h_out_offsets, int out_dtype,
+                                int compute_dtype, void *stream)
+{
+    return chroma_batch_impl(pl, d_audio, 0, h_offsets, n_tracks, center_pad, normalize, d_out, h_out_offsets, out_dtype,
+                             compute_dtype, stream);
+}
+
+extern "C" int afs_chroma_batch_pcm16(afs_chroma_plan *pl, const int16_t *d_pcm, const int64_t *h_offsets, int n_tracks,
+                                      int center_pad, int normalize, void *d_out, const int64_t *h_out_offsets, int out_dtype,
+                                      int compute_dtype, void *stream)
+{
+    return chroma_batch_impl(pl, d_pcm, 1, h_offsets, n_tracks, center_pad, normalize, d_out, h_out_offsets, out_dtype,
+                             compute_dtype, stream);
 }

@@ -109,3 +109,39 @@ def test_wav_to_chroma_from_a_wav_file(chroma, audio, tmp_path):
     d = chroma.wav_to_chroma_diff(path)
     want = np.clip(np.diff(audio["ref_chroma"]), 0, np.inf)
     assert d.shape == want.shape and np.abs(d - want).max() < 2 * TOL_F32
+
+
+def test_pcm16_input_is_bit_identical_to_float_input(chroma, audio, tmp_path):
+    """afs_chroma_batch_pcm16: int16 samples scaled by 1/32768 inside the kernel (librosa.load's int16 rule) give exactly
+    the chroma of the float32 samples — fast fp32 kernel, fp64 parity kernel, raw (un-normalised) output, ragged batch
+    with tracks shorter than a frame, and the mono-WAV loader path."""
+    import wave
+    rng = np.random.default_rng(11)
+    aud = np.load(os.path.join(GOLD, "audio_15s.npz"))
+    mono = aud["ref_i16"][:, 0].astype(np.int16)
+    tracks16 = [mono, mono[1000:1000 + 4096 * 5 + 37], rng.integers(-32768, 32767, size=9001).astype(np.int16),
+                np.zeros(6000, np.int16), mono[:100], mono[3:3 + 4096]]
+    tracksf = [t.astype(np.float32) / np.float32(32768.0) for t in tracks16]
+    for kw in (dict(), dict(compute="fp64"), dict(normalize=False), dict(center=False)):
+        a = chroma.chroma_batch(tracks16, **kw)
+        b = chroma.chroma_batch(tracksf, **kw)
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and np.array_equal(x, y), kw
+    # device-level call with track offsets that are NOT 16-byte aligned (guarded-load path instead of TMA staging)
+    import torch
+    plan = chroma.default_plan()
+    offs = np.array([0, 30002, 30002 + 25000], dtype=np.int64)
+    flat16 = rng.integers(-20000, 20000, size=int(offs[-1])).astype(np.int16)
+    o16, f16 = plan.run(torch.from_numpy(flat16).cuda(), offs)
+    o32, f32 = plan.run(torch.from_numpy(flat16.astype(np.float32) / np.float32(32768.0)).cuda(), offs)
+    assert np.array_equal(f16, f32) and torch.equal(o16, o32)
+    # mono PCM16 WAV: the loader hands int16 to the kernel
+    path = os.path.join(str(tmp_path), "mono.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(22050)
+        w.writeframes(mono.astype("<i2").tobytes())
+    pcm, rate = chroma.load_wav_pcm16(path)
+    assert rate == 22050 and pcm.dtype == np.int16 and np.array_equal(pcm, mono)
+    assert np.array_equal(chroma.wav_to_chroma(path), chroma.wav_samples_to_chroma(tracksf[0]))
