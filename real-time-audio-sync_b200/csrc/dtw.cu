@@ -3,7 +3,7 @@
 // Replaces dtw.DTW (reference dtw.py:5-53).  The N x M cost and accumulated-cost
 // matrices are never written to HBM: the cosine cost 1 - a_i.b_j (K = 12) is
 // computed inline inside a skewed warp wavefront, and only a 2-bit direction code
-// per cell is stored (0 = left (i,j-1), 1 = up (i-1,j), 2 = diag; dtw.py:30,38-40).
+// per cell is stored (0 = left (i,j-1), 1 = up (i-1,j), 2 or 3 = diag; dtw.py:30,38-40).
 //
 // Work decomposition
 //   band   = 128 consecutive rows (i) of one pair, swept over all N columns by ONE warp;
@@ -31,6 +31,7 @@
 #include <math_constants.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include <vector>
 
@@ -94,6 +95,12 @@ template <> struct Arith<double> {
         return v;
     }
     static __device__ __forceinline__ void sts(uint32_t saddr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(saddr), "d"(v) : "memory"); }
+    // out = a < b ? a : b;  if (a < b) bits |= bit   (bit is a compile-time constant after unrolling)
+    static __device__ __forceinline__ void min_first(double &out, uint32_t &bits, double a, double b, uint32_t bit)
+    {
+        asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %2, %3;\n\tselp.f64 %0, %2, %3, p;\n\t@p or.b32 %1, %1, %4;\n\t}"
+            : "=d"(out), "+r"(bits) : "d"(a), "d"(b), "r"(bit));
+    }
 };
 template <> struct Arith<float> {
     static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
@@ -118,6 +125,11 @@ template <> struct Arith<float> {
         return v;
     }
     static __device__ __forceinline__ void sts(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
+    static __device__ __forceinline__ void min_first(float &out, uint32_t &bits, float a, float b, uint32_t bit)
+    {
+        asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %2, %3;\n\tselp.f32 %0, %2, %3, p;\n\t@p or.b32 %1, %1, %4;\n\t}"
+            : "=f"(out), "+r"(bits) : "f"(a), "f"(b), "r"(bit));
+    }
 };
 
 template <typename T>
@@ -223,7 +235,7 @@ __global__ void dtw_pack_b_kernel(const T *__restrict__ b, T *__restrict__ bt, c
     for (int k = 0; k < S; k++) dst[k] = (k < kF && j < pm.N) ? __ldg(src + (int64_t)k * pm.N + j) : (T)0;
 }
 
-template <typename T, bool DENSE, int U>
+template <typename T, bool DENSE, int U, bool ALL>
 __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane, const int band, const DtwPair &pm,
                                          const uint32_t ring_s, const uint32_t ubuf_s, T *obuf, const bool feeds_next,
                                          uint32_t &dw, const DtwArgs<T> &args, const double base)
@@ -237,7 +249,8 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
     // lane 0 takes it from the band above (staged in ubuf)
     T up = __shfl_up_sync(full, L.bottom, 1);
     if (lane == 0) up = A::lds(ubuf_s + (s & 31) * (int)sizeof(T));
-    const bool act = (unsigned)j < (unsigned)N;
+    // ALL: the caller guarantees 0 <= j < N for every lane (steady state): the commit selects fold away
+    const bool act = ALL ? true : ((unsigned)j < (unsigned)N);
     if (DENSE) {
         if (!act) return;
     }
@@ -259,18 +272,17 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
     }
     T diag = L.up_prev;
     T upv = up;
-    uint32_t nib = 0;
 #pragma unroll
     for (int r = 0; r < kRows; r++) {
         T x = A::add(L.left[r], c[r]);                  // (i, j-1)   dtw.py:35
         T y = A::add(upv, c[r]);                        // (i-1, j)   dtw.py:36
         T z = A::fma((T)2, c[r], diag);                 // (i-1, j-1) dtw.py:37 (2c exact)
-        const bool yx = y < x;                          // np.argmin: first minimum wins
-        T m = yx ? y : x;
-        const bool zm = z < m;
-        T v = zm ? z : m;
-        uint32_t code = zm ? 2u : (yx ? 1u : 0u);
-        nib |= code << (2 * r);
+        // np.argmin: first minimum wins (strict <).  The direction code is the two raw predicates (bit 0: up
+        // beat left, bit 1: diag beat both; 3 reads as diag in the backtrack), OR-ed into dw by ONE predicated
+        // instruction each (inline PTX: the compiler otherwise builds a P2R / SEL / LOP3 chain, ~18 per step)
+        T m, v;
+        A::min_first(m, dw, y, x, 1u << (8 * U + 2 * r));      // m = y < x ? y : x
+        A::min_first(v, dw, z, m, 2u << (8 * U + 2 * r));      // v = z < m ? z : m
         diag = L.left[r];
         L.left[r] = act ? v : L.left[r];
         upv = v;
@@ -284,7 +296,6 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
     }
     L.up_prev = act ? up : L.up_prev;
     L.bottom = L.left[kRows - 1];
-    dw |= nib << (8 * U);
     if (feeds_next && lane == 31 && act) obuf[s & 31] = L.bottom;
 }
 
@@ -451,20 +462,26 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
                 pref = make_uint4(0u, 0u, 0u, 0u);
                 if (col + 32 < N) pref = ld_record(brow_prev + col + 32);
             }
+            auto run_group = [&](auto all_tag) {
+                constexpr bool ALL = decltype(all_tag)::value;
 #pragma unroll 1
-            for (int g4 = 0; g4 < 8; g4++) {
-                const int s = s0 + g4 * 4;
-                uint32_t dw = 0;
-                dtw_step<T, DENSE, 0>(L, s + 0, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
-                dtw_step<T, DENSE, 1>(L, s + 1, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
-                dtw_step<T, DENSE, 2>(L, s + 2, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
-                dtw_step<T, DENSE, 3>(L, s + 3, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
-                d0 = d1; d1 = d2; d2 = d3; d3 = dw;
-                if ((g4 & 3) == 3) {
-                    const int cbp = s >> 4;
-                    __stcs(dirp + (int64_t)cbp * pm.gpad, make_uint4(d0, d1, d2, d3));
+                for (int g4 = 0; g4 < 8; g4++) {
+                    const int s = s0 + g4 * 4;
+                    uint32_t dw = 0;
+                    dtw_step<T, DENSE, 0, ALL>(L, s + 0, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
+                    dtw_step<T, DENSE, 1, ALL>(L, s + 1, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
+                    dtw_step<T, DENSE, 2, ALL>(L, s + 2, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
+                    dtw_step<T, DENSE, 3, ALL>(L, s + 3, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
+                    d0 = d1; d1 = d2; d2 = d3; d3 = dw;
+                    if ((g4 & 3) == 3) {
+                        const int cbp = s >> 4;
+                        __stcs(dirp + (int64_t)cbp * pm.gpad, make_uint4(d0, d1, d2, d3));
+                    }
                 }
-            }
+            };
+            // steady state: every lane's column s - lane lies in [1, N) for all 32 steps of the group
+            if (s0 >= 32 && s0 + 32 <= N) run_group(std::true_type{});
+            else run_group(std::false_type{});
             if (feeds_next) {
                 // slots 0..31 hold lane 31's columns s0-31 .. s0
                 __syncwarp();
