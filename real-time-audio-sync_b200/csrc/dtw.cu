@@ -45,6 +45,7 @@ constexpr int kBandRows = 32 * kRows;
 constexpr int kWarpsPerBlock = 4;
 constexpr int kChunkCols = 32;   // columns per staged chunk of seq_b
 constexpr int kRingSlots = 4;    // chunks resident per warp
+constexpr int kSlackGroups = 0;  // default extra band-to-band distance, in groups of 32 columns (see the kernel)
 
 // packed seq_b: elements per column.  fp64: 12 + 2 pad = 112 B (lane stride 28 words: the 8
 // lanes of a 128-bit shared-load phase hit 8 distinct 4-word bank groups); fp32: 12 = 48 B
@@ -151,6 +152,7 @@ struct DtwArgs {
     const int *in_flag;    // [nbands] raised by the left stripe when leftb rows of a band are valid (null: valid already)
     int *out_flag;         // [nbands] raised for the right stripe (may be peer-mapped; null: none)
     unsigned long long wait_ns;   // bound on the in_flag wait
+    int slack_groups;             // extra distance (groups of 32 columns) a band keeps from the band above
 };
 
 // Per-lane wavefront state.
@@ -235,13 +237,37 @@ __global__ void dtw_pack_b_kernel(const T *__restrict__ b, T *__restrict__ bt, c
     for (int k = 0; k < S; k++) dst[k] = (k < kF && j < pm.N) ? __ldg(src + (int64_t)k * pm.N + j) : (T)0;
 }
 
-template <typename T, bool DENSE, int U, bool ALL>
-__device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane, const int band, const DtwPair &pm,
-                                         const uint32_t ring_s, const uint32_t ubuf_s, T *obuf, const bool feeds_next,
-                                         uint32_t &dw, const DtwArgs<T> &args, const double base)
+// cost of the lane's rows against column (s - lane): c[r] = 1 - a_r . b_j   (dtw.py:11; sequential fma chain over
+// k per row = the dgemm rounding order the oracle pins).  The four row chains are independent of each other and
+// of the DP state, which is what lets dtw_step run them in the shadow of the previous column's DP chain.
+template <typename T>
+__device__ __forceinline__ void dtw_cost(const Lane<T> &L, const int s, const int lane, const uint32_t ring_s, T (&c)[kRows])
 {
     using A = Arith<T>;
     constexpr int S = ColStride<T>::value;
+    const int j = s - lane;
+    T bk[kF];
+    A::load_col(ring_s + (j & (kRingSlots * kChunkCols - 1)) * (S * (int)sizeof(T)), bk);
+#pragma unroll
+    for (int r = 0; r < kRows; r++) c[r] = A::mul(L.ar[r][0], bk[0]);
+#pragma unroll
+    for (int k = 1; k < kF; k++)
+#pragma unroll
+        for (int r = 0; r < kRows; r++) c[r] = A::fma(L.ar[r][k], bk[k], c[r]);
+#pragma unroll
+    for (int r = 0; r < kRows; r++) c[r] = A::sub((T)1, c[r]);
+}
+
+// One wavefront step, software-pipelined: on entry c[] holds the costs of THIS step's column (computed during the
+// previous step); the costs of the next step's column are computed first (48 independent-chain FMAs, throughput
+// work) so that the scheduler can interleave them with this step's DP recurrence (a serial chain of
+// add / compare / select through the four rows, latency work).
+template <typename T, bool DENSE, int U, bool ALL>
+__device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane, const int band, const DtwPair &pm,
+                                         const uint32_t ring_s, const uint32_t ubuf_s, T *obuf, const bool feeds_next,
+                                         uint32_t &dw, const DtwArgs<T> &args, const double base, T (&c)[kRows])
+{
+    using A = Arith<T>;
     const unsigned full = 0xffffffffu;
     const int N = pm.N;
     const int j = s - lane;
@@ -249,27 +275,12 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
     // lane 0 takes it from the band above (staged in ubuf)
     T up = __shfl_up_sync(full, L.bottom, 1);
     if (lane == 0) up = A::lds(ubuf_s + (s & 31) * (int)sizeof(T));
-    // ALL: the caller guarantees 0 <= j < N for every lane (steady state): the commit selects fold away
+    // ALL: the caller guarantees 0 <= j < N for every lane (steady state): the commit selects fold away.
+    // Otherwise lanes outside [0, N) (start-up / drain of the skew) compute on whatever the ring holds and
+    // simply do not commit (branch-free: the unrolled steps stay one basic block).
     const bool act = ALL ? true : ((unsigned)j < (unsigned)N);
-    if (DENSE) {
-        if (!act) return;
-    }
-    // Batch kernels are branch-free: lanes outside [0, N) (start-up / drain of the skew) compute on whatever
-    // the ring holds and simply do not commit.  The four unrolled steps then form one basic block, so the
-    // next column's loads and dot products can be scheduled under the current column's dependent DP chain.
-    T c[kRows];
-    {
-        T bk[kF];
-        A::load_col(ring_s + (j & (kRingSlots * kChunkCols - 1)) * (S * (int)sizeof(T)), bk);
-#pragma unroll
-        for (int r = 0; r < kRows; r++) c[r] = A::mul(L.ar[r][0], bk[0]);
-#pragma unroll
-        for (int k = 1; k < kF; k++)
-#pragma unroll
-            for (int r = 0; r < kRows; r++) c[r] = A::fma(L.ar[r][k], bk[k], c[r]);
-#pragma unroll
-        for (int r = 0; r < kRows; r++) c[r] = A::sub((T)1, c[r]);    // dtw.py:11
-    }
+    T cn[kRows];
+    dtw_cost<T>(L, s + 1, lane, ring_s, cn);
     T diag = L.up_prev;
     T upv = up;
 #pragma unroll
@@ -288,7 +299,7 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
         upv = v;
         if (DENSE) {
             const int64_t i = (int64_t)band * kBandRows + lane * kRows + r;
-            if (i < pm.M) {
+            if (act && i < pm.M) {
                 args.dense_cost[i * N + j] = c[r];
                 args.dense_acc[i * N + j] = (T)((double)v + base);
             }
@@ -297,6 +308,8 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
     L.up_prev = act ? up : L.up_prev;
     L.bottom = L.left[kRows - 1];
     if (feeds_next && lane == 31 && act) obuf[s & 31] = L.bottom;
+#pragma unroll
+    for (int r = 0; r < kRows; r++) c[r] = cn[r];
 }
 
 template <typename T, bool DENSE>
@@ -408,8 +421,29 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
         // fp32 mode: lane state holds OFFSETS against a per-band fp64 base that is moved every 32
         // steps (min-plus recurrences are shift invariant), so offsets stay O(band height) and the
         // accumulated cost keeps ~1e-7 relative accuracy over 4e4 additions.  fp64 mode: base == 0.
+        // Slack between consecutive bands of a pair.  A band can follow the one above at a distance of two
+        // groups (64 steps), but a band running AT that distance stalls on every hiccup of its producer, and
+        // the stall propagates down the whole chain of in-flight bands.  Starting `slack` groups later costs
+        // that many steps once per band of the first wave and lets the chain absorb jitter afterwards
+        // (later waves inherit the spacing: slots free up in the rhythm the bands finish).
+        if (band > 0 && args.slack_groups > 0) {
+            const int wcol = min(N - 1, 31 + 32 * args.slack_groups);
+            if (lane == 0) {
+                for (;;) {
+                    const uint4 r = ld_record(brow_prev + wcol);
+                    if (r.y == tag_prev && r.w == tag_prev) break;
+                    __nanosleep(200);
+                }
+            }
+            __syncwarp();
+        }
         double base = 0.0;
         uint4 pref = make_uint4(0u, 0u, 0u, 0u);
+        // software pipeline prologue: costs of column 0 (chunk 0 must have landed)
+        T cst[kRows];
+        mbar_wait(&sm.mbar[0], phase_bits & 1u);
+        phase_bits ^= 1u;
+        dtw_cost<T>(L, 0, lane, ring_s, cst);
         uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
         for (int s0 = 0; s0 < pm.nsteps; s0 += 32) {
             const int c0 = s0 >> 5;
@@ -427,9 +461,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
                     L.bottom -= lo;
                 }
             }
-            // ---- chunk c0 of seq_b must have landed; then put chunk c0+2 in flight ----
-            if (c0 < nchunks) {
-                const int slot = c0 & (kRingSlots - 1);
+            // ---- chunk c0+1 of seq_b must have landed (the last step of this group already computes the
+            // costs of the next group's first column); then put chunk c0+2 in flight ----
+            if (c0 + 1 < nchunks) {
+                const int slot = (c0 + 1) & (kRingSlots - 1);
                 mbar_wait(&sm.mbar[slot], (phase_bits >> slot) & 1u);
                 phase_bits ^= 1u << slot;      // every fill of a slot is waited for exactly once, in order
             }
@@ -468,10 +503,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
                 for (int g4 = 0; g4 < 8; g4++) {
                     const int s = s0 + g4 * 4;
                     uint32_t dw = 0;
-                    dtw_step<T, DENSE, 0, ALL>(L, s + 0, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
-                    dtw_step<T, DENSE, 1, ALL>(L, s + 1, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
-                    dtw_step<T, DENSE, 2, ALL>(L, s + 2, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
-                    dtw_step<T, DENSE, 3, ALL>(L, s + 3, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base);
+                    dtw_step<T, DENSE, 0, ALL>(L, s + 0, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base, cst);
+                    dtw_step<T, DENSE, 1, ALL>(L, s + 1, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base, cst);
+                    dtw_step<T, DENSE, 2, ALL>(L, s + 2, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base, cst);
+                    dtw_step<T, DENSE, 3, ALL>(L, s + 3, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base, cst);
                     d0 = d1; d1 = d2; d2 = d3; d3 = dw;
                     if ((g4 & 3) == 3) {
                         const int cbp = s >> 4;
@@ -796,6 +831,8 @@ static int launch_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b,
     args.in_flag = in_flag;
     args.out_flag = out_flag;
     args.wait_ns = kStripeWaitNs;
+    args.slack_groups = kSlackGroups;
+    if (const char *sg = getenv("AFS_DTW_SLACK")) args.slack_groups = atoi(sg);      // tuning knob
     if (in_flag != nullptr) {
         const char *ms = getenv("AFS_STRIPE_WAIT_MS");
         if (ms != nullptr && atoll(ms) > 0) args.wait_ns = (unsigned long long)atoll(ms) * 1000000ull;
