@@ -267,6 +267,7 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
                                          const uint32_t ring_s, const uint32_t ubuf_s, T *obuf, const bool feeds_next,
                                          uint32_t &dw, const DtwArgs<T> &args, const double base, T (&c)[kRows])
 {
+    // ubuf_s / obuf point at the slots of the current group of FOUR steps (s & ~3): slot U is this step's
     using A = Arith<T>;
     const unsigned full = 0xffffffffu;
     const int N = pm.N;
@@ -274,7 +275,7 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
     // inputs for the lane's first row: value under the previous lane's last row, one step ago;
     // lane 0 takes it from the band above (staged in ubuf)
     T up = __shfl_up_sync(full, L.bottom, 1);
-    if (lane == 0) up = A::lds(ubuf_s + (s & 31) * (int)sizeof(T));
+    if (lane == 0) up = A::lds(ubuf_s + U * (int)sizeof(T));
     // ALL: the caller guarantees 0 <= j < N for every lane (steady state): the commit selects fold away.
     // Otherwise lanes outside [0, N) (start-up / drain of the skew) compute on whatever the ring holds and
     // simply do not commit (branch-free: the unrolled steps stay one basic block).
@@ -307,7 +308,7 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
     }
     L.up_prev = act ? up : L.up_prev;
     L.bottom = L.left[kRows - 1];
-    if (feeds_next && lane == 31 && act) obuf[s & 31] = L.bottom;
+    if (feeds_next && lane == 31 && act) obuf[U] = L.bottom;
 #pragma unroll
     for (int r = 0; r < kRows; r++) c[r] = cn[r];
 }
@@ -503,10 +504,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
                 for (int g4 = 0; g4 < 8; g4++) {
                     const int s = s0 + g4 * 4;
                     uint32_t dw = 0;
-                    dtw_step<T, DENSE, 0, ALL>(L, s + 0, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base, cst);
-                    dtw_step<T, DENSE, 1, ALL>(L, s + 1, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base, cst);
-                    dtw_step<T, DENSE, 2, ALL>(L, s + 2, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base, cst);
-                    dtw_step<T, DENSE, 3, ALL>(L, s + 3, lane, band, pm, ring_s, ubuf_s, sm.obuf, feeds_next, dw, args, base, cst);
+                    const uint32_t ubuf_g = ubuf_s + g4 * 4 * (int)sizeof(T);     // s0 is a multiple of 32: slot = s & 31
+                    T *obuf_g = sm.obuf + g4 * 4;
+                    dtw_step<T, DENSE, 0, ALL>(L, s + 0, lane, band, pm, ring_s, ubuf_g, obuf_g, feeds_next, dw, args, base, cst);
+                    dtw_step<T, DENSE, 1, ALL>(L, s + 1, lane, band, pm, ring_s, ubuf_g, obuf_g, feeds_next, dw, args, base, cst);
+                    dtw_step<T, DENSE, 2, ALL>(L, s + 2, lane, band, pm, ring_s, ubuf_g, obuf_g, feeds_next, dw, args, base, cst);
+                    dtw_step<T, DENSE, 3, ALL>(L, s + 3, lane, band, pm, ring_s, ubuf_g, obuf_g, feeds_next, dw, args, base, cst);
                     d0 = d1; d1 = d2; d2 = d3; d3 = dw;
                     if ((g4 & 3) == 3) {
                         const int cbp = s >> 4;
