@@ -558,6 +558,23 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
     }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Backtrack helper.  The walk leaves the tile (band, cb8) to the left (band, cb8-1) or upwards; going up into the
+// band above, the column skew (g & 31) jumps from 0 to 31, so the tile above is (band-1, cb8) or (band-1, cb8+1).
+// Pull those three tiles (written with a streaming hint by K2, so they sit in HBM) into L2 while lane 0 walks the
+// current one.  A tile is 8 rows of 512 contiguous bytes = 32 lines of 128 B: one line per lane.
+__device__ __forceinline__ void prefetch_next_tiles(const uint4 *dunits, int gpad, int ncbp, int band, int cb8, int lane)
+{
+    const int q = lane >> 2, line8 = (lane & 3) * 8;
+    const int cbl = (cb8 - 1) * 8 + q, cbc = cb8 * 8 + q, cbr = (cb8 + 1) * 8 + q;
+    if (cb8 > 0) prefetch_l2(dunits + (int64_t)cbl * gpad + band * 32 + line8);
+    if (band > 0) {
+        if (cbc < ncbp) prefetch_l2(dunits + (int64_t)cbc * gpad + (band - 1) * 32 + line8);
+        if (cbr < ncbp) prefetch_l2(dunits + (int64_t)cbr * gpad + (band - 1) * 32 + line8);
+    }
+}
+
 // K3 for one stripe of a column-striped pair: walk from (i0, j0) (stripe-local column) until the
 // path leaves the stripe through its left edge (or reaches (0,0) in the first stripe).  Points are
 // written back-to-front with GLOBAL column indices (col0 + j).  exit_i = row at which the walk
@@ -587,6 +604,7 @@ __global__ void __launch_bounds__(32) dtw_backtrack_stripe_kernel(const DtwPair 
             if (cbp < ncbp) v = __ldcs(dunits + (int64_t)cbp * pm.gpad + band * 32 + lane);
             s_tile[q * 32 + lane] = v;
         }
+        prefetch_next_tiles(dunits, pm.gpad, ncbp, band, cb8, lane);
         __syncwarp();
         if (lane == 0) {
             while (!done) {
@@ -653,6 +671,7 @@ __global__ void __launch_bounds__(kBtWarps * 32) dtw_backtrack_kernel(const DtwP
             if (cbp < ncbp) v = __ldcs(dunits + (int64_t)cbp * pm.gpad + band * 32 + lane);
             s_tile[w][q * 32 + lane] = v;
         }
+        prefetch_next_tiles(dunits, pm.gpad, ncbp, band, cb8, lane);
         __syncwarp();
         if (lane == 0) {
             while (i > 0 || j > 0) {
