@@ -45,6 +45,7 @@ constexpr int kBandRows = 32 * kRows;
 constexpr int kWarpsPerBlock = 4;
 constexpr int kChunkCols = 32;   // columns per staged chunk of seq_b
 constexpr int kRingSlots = 4;    // chunks resident per warp
+constexpr int kMirrorCols = 4;   // ring columns 0..3 repeated after column 127 (one unrolled group of steps looks 4 ahead)
 constexpr int kSlackGroups = 0;  // default extra band-to-band distance, in groups of 32 columns (see the kernel)
 
 // packed seq_b: elements per column.  fp64: 12 + 2 pad = 112 B (lane stride 28 words: the 8
@@ -76,14 +77,14 @@ template <> struct Arith<double> {
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
     // one packed column (12 values) from shared memory: 6 x ld.shared.v2.f64 at immediate offsets
-    static __device__ __forceinline__ void load_col(uint32_t saddr, double (&bk)[kF])
+    template <int BASE> static __device__ __forceinline__ void load_col(uint32_t saddr, double (&bk)[kF])
     {
-        lds2<0>(saddr, bk[0], bk[1]);
-        lds2<16>(saddr, bk[2], bk[3]);
-        lds2<32>(saddr, bk[4], bk[5]);
-        lds2<48>(saddr, bk[6], bk[7]);
-        lds2<64>(saddr, bk[8], bk[9]);
-        lds2<80>(saddr, bk[10], bk[11]);
+        lds2<BASE + 0>(saddr, bk[0], bk[1]);
+        lds2<BASE + 16>(saddr, bk[2], bk[3]);
+        lds2<BASE + 32>(saddr, bk[4], bk[5]);
+        lds2<BASE + 48>(saddr, bk[6], bk[7]);
+        lds2<BASE + 64>(saddr, bk[8], bk[9]);
+        lds2<BASE + 80>(saddr, bk[10], bk[11]);
     }
     template <int OFF> static __device__ __forceinline__ void lds2(uint32_t saddr, double &x, double &y)
     {
@@ -109,11 +110,11 @@ template <> struct Arith<float> {
     static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-    static __device__ __forceinline__ void load_col(uint32_t saddr, float (&bk)[kF])
+    template <int BASE> static __device__ __forceinline__ void load_col(uint32_t saddr, float (&bk)[kF])
     {
-        lds4<0>(saddr, bk[0], bk[1], bk[2], bk[3]);
-        lds4<16>(saddr, bk[4], bk[5], bk[6], bk[7]);
-        lds4<32>(saddr, bk[8], bk[9], bk[10], bk[11]);
+        lds4<BASE + 0>(saddr, bk[0], bk[1], bk[2], bk[3]);
+        lds4<BASE + 16>(saddr, bk[4], bk[5], bk[6], bk[7]);
+        lds4<BASE + 32>(saddr, bk[8], bk[9], bk[10], bk[11]);
     }
     template <int OFF> static __device__ __forceinline__ void lds4(uint32_t saddr, float &x, float &y, float &z, float &w)
     {
@@ -216,7 +217,9 @@ __device__ __forceinline__ void st_record(uint4 *p, uint4 v)
 
 template <typename T>
 struct WarpSmem {
-    T ring[kRingSlots * kChunkCols * ColStride<T>::value];   // column (j & 127) at ring + (j & 127) * stride
+    // column (j & 127) at ring + (j & 127) * stride; the first kMirrorCols columns are mirrored behind the ring so
+    // that a lane can address the next few columns from one base without wrapping (immediate offsets)
+    T ring[(kRingSlots * kChunkCols + kMirrorCols) * ColStride<T>::value];
     T ubuf[32];
     T obuf[32];
     uint64_t mbar[kRingSlots];
@@ -240,14 +243,14 @@ __global__ void dtw_pack_b_kernel(const T *__restrict__ b, T *__restrict__ bt, c
 // cost of the lane's rows against column (s - lane): c[r] = 1 - a_r . b_j   (dtw.py:11; sequential fma chain over
 // k per row = the dgemm rounding order the oracle pins).  The four row chains are independent of each other and
 // of the DP state, which is what lets dtw_step run them in the shadow of the previous column's DP chain.
-template <typename T>
-__device__ __forceinline__ void dtw_cost(const Lane<T> &L, const int s, const int lane, const uint32_t ring_s, T (&c)[kRows])
+// col_s: shared-space address of a ring column; COLS_AHEAD: compile-time column offset from it (mirror: no wrap).
+template <typename T, int COLS_AHEAD>
+__device__ __forceinline__ void dtw_cost(const Lane<T> &L, const uint32_t col_s, T (&c)[kRows])
 {
     using A = Arith<T>;
     constexpr int S = ColStride<T>::value;
-    const int j = s - lane;
     T bk[kF];
-    A::load_col(ring_s + (j & (kRingSlots * kChunkCols - 1)) * (S * (int)sizeof(T)), bk);
+    A::template load_col<COLS_AHEAD * S * (int)sizeof(T)>(col_s, bk);
 #pragma unroll
     for (int r = 0; r < kRows; r++) c[r] = A::mul(L.ar[r][0], bk[0]);
 #pragma unroll
@@ -264,7 +267,7 @@ __device__ __forceinline__ void dtw_cost(const Lane<T> &L, const int s, const in
 // add / compare / select through the four rows, latency work).
 template <typename T, bool DENSE, int U, bool ALL>
 __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane, const int band, const DtwPair &pm,
-                                         const uint32_t ring_s, const uint32_t ubuf_s, T *obuf, const bool feeds_next,
+                                         const uint32_t ring_g, const uint32_t ubuf_s, T *obuf, const bool feeds_next,
                                          uint32_t &dw, const DtwArgs<T> &args, const double base, T (&c)[kRows])
 {
     // ubuf_s / obuf point at the slots of the current group of FOUR steps (s & ~3): slot U is this step's
@@ -281,7 +284,7 @@ __device__ __forceinline__ void dtw_step(Lane<T> &L, const int s, const int lane
     // simply do not commit (branch-free: the unrolled steps stay one basic block).
     const bool act = ALL ? true : ((unsigned)j < (unsigned)N);
     T cn[kRows];
-    dtw_cost<T>(L, s + 1, lane, ring_s, cn);
+    dtw_cost<T, U + 1>(L, ring_g, cn);      // ring_g: this lane's column of the group's first step
     T diag = L.up_prev;
     T upv = up;
 #pragma unroll
@@ -319,6 +322,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
     using A = Arith<T>;
     constexpr int S = ColStride<T>::value;
     constexpr uint32_t kChunkBytes = kChunkCols * S * sizeof(T);
+    constexpr uint32_t kMirrorBytes = kMirrorCols * S * sizeof(T);
+    static_assert(kMirrorBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
     extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
@@ -360,9 +365,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
         // stage chunk c of packed seq_b into ring slot (c & 3): one TMA bulk copy
         auto stage = [&](int c) {
             if (c < nchunks && lane == 0) {
-                uint64_t *bar = &sm.mbar[c & (kRingSlots - 1)];
-                mbar_expect_tx(bar, kChunkBytes);
-                bulk_g2s(sm.ring + (c & (kRingSlots - 1)) * (kChunkCols * S), btp + (int64_t)c * (kChunkCols * S), kChunkBytes, bar);
+                const int slot = c & (kRingSlots - 1);
+                uint64_t *bar = &sm.mbar[slot];
+                mbar_expect_tx(bar, slot == 0 ? kChunkBytes + kMirrorBytes : kChunkBytes);
+                bulk_g2s(sm.ring + slot * (kChunkCols * S), btp + (int64_t)c * (kChunkCols * S), kChunkBytes, bar);
+                // slot 0 again behind the ring (first kMirrorCols columns), same barrier
+                if (slot == 0)
+                    bulk_g2s(sm.ring + kRingSlots * kChunkCols * S, btp + (int64_t)c * (kChunkCols * S), kMirrorBytes, bar);
             }
         };
         __syncwarp();          // previous band's readers are done with every slot
@@ -444,7 +453,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
         T cst[kRows];
         mbar_wait(&sm.mbar[0], phase_bits & 1u);
         phase_bits ^= 1u;
-        dtw_cost<T>(L, 0, lane, ring_s, cst);
+        dtw_cost<T, 0>(L, ring_s + ((0 - lane) & (kRingSlots * kChunkCols - 1)) * (S * (int)sizeof(T)), cst);
         uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
         for (int s0 = 0; s0 < pm.nsteps; s0 += 32) {
             const int c0 = s0 >> 5;
@@ -505,11 +514,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) dtw_wavefront_kernel(c
                     const int s = s0 + g4 * 4;
                     uint32_t dw = 0;
                     const uint32_t ubuf_g = ubuf_s + g4 * 4 * (int)sizeof(T);     // s0 is a multiple of 32: slot = s & 31
+                    const uint32_t ring_g = ring_s + ((s - lane) & (kRingSlots * kChunkCols - 1)) * (S * (int)sizeof(T));
                     T *obuf_g = sm.obuf + g4 * 4;
-                    dtw_step<T, DENSE, 0, ALL>(L, s + 0, lane, band, pm, ring_s, ubuf_g, obuf_g, feeds_next, dw, args, base, cst);
-                    dtw_step<T, DENSE, 1, ALL>(L, s + 1, lane, band, pm, ring_s, ubuf_g, obuf_g, feeds_next, dw, args, base, cst);
-                    dtw_step<T, DENSE, 2, ALL>(L, s + 2, lane, band, pm, ring_s, ubuf_g, obuf_g, feeds_next, dw, args, base, cst);
-                    dtw_step<T, DENSE, 3, ALL>(L, s + 3, lane, band, pm, ring_s, ubuf_g, obuf_g, feeds_next, dw, args, base, cst);
+                    dtw_step<T, DENSE, 0, ALL>(L, s + 0, lane, band, pm, ring_g, ubuf_g, obuf_g, feeds_next, dw, args, base, cst);
+                    dtw_step<T, DENSE, 1, ALL>(L, s + 1, lane, band, pm, ring_g, ubuf_g, obuf_g, feeds_next, dw, args, base, cst);
+                    dtw_step<T, DENSE, 2, ALL>(L, s + 2, lane, band, pm, ring_g, ubuf_g, obuf_g, feeds_next, dw, args, base, cst);
+                    dtw_step<T, DENSE, 3, ALL>(L, s + 3, lane, band, pm, ring_g, ubuf_g, obuf_g, feeds_next, dw, args, base, cst);
                     d0 = d1; d1 = d2; d2 = d3; d3 = dw;
                     if ((g4 & 3) == 3) {
                         const int cbp = s >> 4;
