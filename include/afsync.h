@@ -62,7 +62,8 @@ typedef struct afs_dtw_plan afs_dtw_plan;
 int afs_dtw_plan_create(afs_dtw_plan **out, int n_pairs, const int64_t *h_len_a, const int64_t *h_len_b,
                         const int64_t *h_off_a, const int64_t *h_off_b, int n_features, int dtype);
 int afs_dtw_plan_destroy(afs_dtw_plan *plan);
-/* bytes of caller-provided device workspace (direction maps + band hand-off rows) */
+/* bytes of caller-provided device workspace (direction maps + band hand-off rows).  A workspace belongs to ONE plan
+ * and to one launch at a time (accumulate, then backtrack, on the same stream or properly ordered streams). */
 int afs_dtw_plan_workspace_bytes(const afs_dtw_plan *plan, size_t *bytes);
 /* capacity (in (i,j) pairs) of pair p's slot in d_path and its element offset */
 int afs_dtw_plan_path_layout(const afs_dtw_plan *plan, int pair, int64_t *offset, int64_t *capacity);

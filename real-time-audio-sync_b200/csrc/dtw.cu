@@ -30,6 +30,7 @@
 // 32 x 16 B = 512 contiguous bytes every 16 steps (unit index = cbp * gpad + g).
 #include <math_constants.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <type_traits>
 
@@ -241,7 +242,7 @@ __global__ void dtw_pack_b_kernel(const T *__restrict__ b, T *__restrict__ bt, c
 }
 
 // cost of the lane's rows against column (s - lane): c[r] = 1 - a_r . b_j   (dtw.py:11; sequential fma chain over
-// k per row = the dgemm rounding order the oracle pins).  The four row chains are independent of each other and
+// k per row = the rounding order of the reference's dgemm).  The four row chains are independent of each other and
 // of the DP state, which is what lets dtw_step run them in the shadow of the previous column's DP chain.
 // col_s: shared-space address of a ring column; COLS_AHEAD: compile-time column offset from it (mirror: no wrap).
 template <typename T, int COLS_AHEAD>
@@ -853,7 +854,11 @@ static int launch_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b,
         AFS_CUDA(cudaMemsetAsync(args.brow, 0, pl->brow_bytes, st));
         pl->last_ws = ws;
     }
-    pl->epoch = pl->epoch % 250u + 1u;
+    // the epoch that tags this launch's hand-off records comes from one process-wide counter, so that launches of
+    // different plans that were (against the header's advice) pointed at the same workspace cannot validate each
+    // other's stale records
+    static std::atomic<uint32_t> g_epoch{0};
+    pl->epoch = g_epoch.fetch_add(1u) % 250u + 1u;
     args.epoch = pl->epoch;
     args.acc_end = d_acc_end;
     args.dense_cost = static_cast<T *>(dense_cost);
