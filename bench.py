@@ -414,48 +414,17 @@ def bench_dtw(ctx):
     barrier()
     e2e_serial_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
 
-    # The same work as a stream of batches (what a service does): two batches are in flight on two plans / two compute
-    # streams, so the ramp-down of one launch and its backtrack overlap the ramp-up of the next; step k+1's inputs are
-    # uploaded on a copy stream while step k computes, and step k's paths are read back while step k+1 computes.
-    # Every step still moves its own inputs host -> device and its own results device -> host inside the timed region.
-    copy_stream = torch.cuda.Stream()
-    plans2 = [plan, dtw.DtwPlan([Ln] * P, [Ln] * P, dtype=args.dtype)]
-    comp_streams = [torch.cuda.current_stream(), torch.cuda.Stream()]
-    d_in = [(torch.empty_like(d_a), torch.empty_like(d_b)) for _ in range(2)]
+    # The same work as a stream of batches (what a service does), through the public `dtw.DtwPipeline`: two batches are in
+    # flight on two plans / two compute streams, so the ramp-down of one launch and its backtrack overlap the ramp-up of
+    # the next; a batch's inputs are uploaded on a copy stream while the previous batch computes, and its paths are read
+    # back while the next one computes.  Every step still moves its own inputs host -> device and its own results
+    # device -> host inside the timed region.
+    pipe = dtw.DtwPipeline([Ln] * P, [Ln] * P, dtype=args.dtype, depth=2)
 
     def run_pipelined(n):
-        up_done, comp_done, down_done = [None] * n, [None] * n, [None] * n
-
-        def upload(k):
-            with torch.cuda.stream(copy_stream):
-                if k >= 2:
-                    copy_stream.wait_event(comp_done[k - 2])        # the buffer's previous reader has finished
-                d_in[k & 1][0].copy_(h_a, non_blocking=True)
-                d_in[k & 1][1].copy_(h_b, non_blocking=True)
-                up_done[k] = torch.cuda.Event()
-                up_done[k].record(copy_stream)
-
-        upload(0)
-        for k in range(n):
-            if k + 1 < n:
-                upload(k + 1)
-            pk, sk = plans2[k & 1], comp_streams[k & 1]
-            with torch.cuda.stream(sk):
-                sk.wait_event(up_done[k])
-                pk.accumulate(d_in[k & 1][0], d_in[k & 1][1])
-                if k >= 2:
-                    sk.wait_event(down_done[k - 2])                  # this plan's previous paths have left its path buffer
-                pk.backtrack()
-                comp_done[k] = torch.cuda.Event()
-                comp_done[k].record(sk)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(comp_done[k])
-                h_start.copy_(pk.path_start, non_blocking=True)
-                h_len.copy_(pk.path_len, non_blocking=True)
-                h_path.copy_(pk.path, non_blocking=True)
-                h_end.copy_(pk.acc_end, non_blocking=True)
-                down_done[k] = torch.cuda.Event()
-                down_done[k].record(copy_stream)
+        for _ in range(n):
+            pipe.submit(h_a, h_b, as_arrays=False)
+        pipe.drain(as_arrays=False)
         torch.cuda.synchronize()
 
     run_pipelined(2)
@@ -467,8 +436,8 @@ def bench_dtw(ctx):
     e2e_s = max_over_ranks((time.perf_counter() - t0) / pipe_steps)
     e2e_val = cells_rank * world / e2e_s / 1e9
     e2e_serial_val = cells_rank * world / e2e_serial_s / 1e9
-    plans2[1].close()
-    del d_in
+    pipe.close()
+    del pipe
     h2d = int(h_a.numel() * h_a.element_size() + h_b.numel() * h_b.element_size())
     d2h = int(h_path.numel() * 4 + h_start.numel() * 4 + h_len.numel() * 4 + h_end.numel() * 8)
     # ---- the other arithmetic mode on the same data (kernel only): fp32 offsets against fp64 bases ----
@@ -534,9 +503,9 @@ def bench_dtw(ctx):
         "fp32_mode": other,
         "wall_s_timed_region": t_wall,
         "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": 2 * e2e_steps,
-                "mode": "stream of batches: two batches in flight on two plans / compute streams; upload of step k+1 and read-back of "
-                        "step k overlap the neighbouring step's kernels (copy stream + events); every step's own copies are inside "
-                        "the timed region",
+                "mode": "dtw.DtwPipeline(depth=2): a stream of batches, two in flight on two plans / compute streams; a batch's "
+                        "upload and read-back overlap the neighbouring batch's kernels (copy stream + events); every step's own "
+                        "copies are inside the timed region",
                 "serial_value": e2e_serial_val,
                 "serial_note": "one batch at a time: upload, K2, K3, read-back, synchronize"},
         "gpu_launches": int(launches),

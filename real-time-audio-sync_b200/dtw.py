@@ -108,6 +108,96 @@ class DtwPlan(object):
         return out
 
 
+class DtwPipeline(object):
+    """A stream of same-shape batches with ``depth`` batches in flight (default 2).
+
+    Each slot owns a plan (workspace, path buffers), a compute stream, device input buffers and pinned host result
+    buffers.  ``submit(h_a, h_b)`` uploads one batch from (preferably pinned) host tensors on an upload stream and launches
+    K2 + K3 on the slot's compute stream; the read-back of its paths is queued behind them on a download stream.  It
+    returns the results of the batch that previously used the slot (``None`` while the pipeline fills); ``drain()``
+    returns what is still in flight.  Uploads, kernels and read-backs of neighbouring batches overlap, and the
+    ramp-down of one launch overlaps the ramp-up of the next.  Results: ``(paths, acc_end)`` as ``dtw_batch`` gives."""
+
+    def __init__(self, lens_a, lens_b, dtype="fp64", depth=2, device=None):
+        nat.require_cuda()
+        self.depth = int(depth)
+        assert self.depth >= 1
+        self.plans = [DtwPlan(lens_a, lens_b, dtype=dtype, device=device) for _ in range(self.depth)]
+        p0 = self.plans[0]
+        self.device = p0.device
+        n_a, n_b = int((p0.lens_a * 12).sum()), int((p0.lens_b * 12).sum())
+        with torch.cuda.device(self.device):
+            self.copy_stream = torch.cuda.Stream()       # host -> device
+            self.down_stream = torch.cuda.Stream()       # device -> host (its own stream: a read-back waits for its
+                                                         # batch's kernels and must not hold up the next upload)
+            self.streams = [torch.cuda.Stream() for _ in range(self.depth)]
+        self.d_a = [torch.empty(n_a, dtype=p0.torch_dtype, device=self.device) for _ in range(self.depth)]
+        self.d_b = [torch.empty(n_b, dtype=p0.torch_dtype, device=self.device) for _ in range(self.depth)]
+        self.h_path = [torch.empty((p0.path_total, 2), dtype=torch.int32).pin_memory() for _ in range(self.depth)]
+        self.h_start = [torch.empty(p0.n_pairs, dtype=torch.int32).pin_memory() for _ in range(self.depth)]
+        self.h_len = [torch.empty(p0.n_pairs, dtype=torch.int32).pin_memory() for _ in range(self.depth)]
+        self.h_end = [torch.empty(p0.n_pairs, dtype=torch.float64).pin_memory() for _ in range(self.depth)]
+        self.done = [None] * self.depth          # read-back complete (copy stream)
+        self.computed = [None] * self.depth      # K2 + K3 complete (compute stream)
+        self.k = 0
+        self.h2d_bytes = (n_a + n_b) * self.d_a[0].element_size()
+        self.d2h_bytes = p0.path_total * 8 + p0.n_pairs * 16
+
+    def _collect(self, q, as_arrays=True):
+        self.done[q].synchronize()
+        self.done[q] = None
+        if not as_arrays:
+            return self.h_path[q], self.h_start[q], self.h_len[q], self.h_end[q]
+        plan, flat = self.plans[q], self.h_path[q].numpy()
+        start, length = self.h_start[q].numpy(), self.h_len[q].numpy()
+        paths = []
+        for p in range(plan.n_pairs):
+            s0 = int(plan.path_off[p] + start[p])
+            paths.append(flat[s0 : s0 + int(length[p])].astype(np.int64))
+        return paths, self.h_end[q].numpy().copy()
+
+    def submit(self, h_a, h_b, as_arrays=True):
+        q = self.k % self.depth
+        self.k += 1
+        prev = self._collect(q, as_arrays) if self.done[q] is not None else None
+        plan, cs, st = self.plans[q], self.copy_stream, self.streams[q]
+        with torch.cuda.stream(cs):
+            if self.computed[q] is not None:
+                cs.wait_event(self.computed[q])              # the slot's previous kernels no longer read its inputs
+            self.d_a[q].copy_(h_a.reshape(-1), non_blocking=True)
+            self.d_b[q].copy_(h_b.reshape(-1), non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(cs)
+        with torch.cuda.stream(st):
+            st.wait_event(up)
+            plan.accumulate(self.d_a[q], self.d_b[q])
+            plan.backtrack()                                 # the slot's previous read-back was collected above
+            self.computed[q] = torch.cuda.Event()
+            self.computed[q].record(st)
+        ds = self.down_stream
+        with torch.cuda.stream(ds):
+            ds.wait_event(self.computed[q])
+            self.h_start[q].copy_(plan.path_start, non_blocking=True)
+            self.h_len[q].copy_(plan.path_len, non_blocking=True)
+            self.h_path[q].copy_(plan.path, non_blocking=True)
+            self.h_end[q].copy_(plan.acc_end, non_blocking=True)
+            self.done[q] = torch.cuda.Event()
+            self.done[q].record(ds)
+        return prev
+
+    def drain(self, as_arrays=True):
+        out = []
+        for i in range(self.depth):
+            q = (self.k + i) % self.depth
+            if self.done[q] is not None:
+                out.append(self._collect(q, as_arrays))
+        return out
+
+    def close(self):
+        for p in self.plans:
+            p.close()
+
+
 def dtw_batch(seqs_a, seqs_b, dtype="fp64"):
     """Align many pairs in one launch.  seqs_a/seqs_b: lists of (12, len) arrays.
     Returns (paths, acc_end) with paths a list of int64 (P,2) arrays."""
