@@ -139,3 +139,36 @@ def test_ragged_batch_vs_oracle(mods, orc):
     for s in range(4):
         assert np.array_equal(got[s], oracles[s].path_array()), s
     b.close()
+
+
+@pytest.mark.parametrize("kind,c,mr", [("otw", 7, 2), ("otw", 40, 3), ("livenote_v2", 7, 3), ("livenote_v2", 33, 5),
+                                        ("livenote", 12, 3), ("livenote_v2", 100, 2)])
+def test_fuzz_many_ragged_streams(mods, orc, kind, c, mr):
+    """48 streams with random reference lengths (some shorter than c, some one frame long), each fed a live sequence of
+    different tempo until it stops or the live ends, in one batch: every stream's path equals the oracle's."""
+    import torch
+    rng = np.random.default_rng(c * 131 + mr)
+    n = 48
+    ref_lens = [int(x) for x in rng.integers(1, 260, size=n)]
+    ref_lens[0], ref_lens[1], ref_lens[2] = 1, 2, c + 1
+    refs = [chroma_like(rng, m) for m in ref_lens]
+    T = 320
+    lives = [warped_copy(rng, r, T) if r.shape[1] > 4 else chroma_like(rng, T) for r in refs]
+    b = mods["batch"].OtwBatch(refs, c, mr, kind=kind)
+    params = {"c": c, "max_run_count": mr, "search_band_width": c}      # the reference's two spellings of the band width
+    ocls = {"otw": orc.OnlineTimeWarping, "livenote_v2": orc.LiveNoteV2, "livenote": orc.LiveNote}[kind]
+    oracles = [ocls(r, dict(params)) for r in refs]
+    done = [False] * n
+    for k in range(T):
+        fr = np.stack([lv[:, k] for lv in lives])
+        st, _, _ = b.step_device(torch.from_numpy(fr).cuda().reshape(1, n, 12))
+        st = st.cpu().numpy()[0]
+        for s in range(n):
+            if not done[s]:
+                r = oracles[s].insert(lives[s][:, k])
+                assert (r == "stop") == (st[s] == 1), (k, s, ref_lens[s])
+                done[s] = r == "stop"
+    got = b.paths()
+    for s in range(n):
+        assert np.array_equal(got[s], oracles[s].path_array()), (s, ref_lens[s])
+    b.close()
