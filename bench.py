@@ -124,7 +124,6 @@ def cpu_dtw_baseline(seconds=12.0, threads=None):
     """Oracle C port (oracle/afs_oracle.c, dtw.py:5-53 arithmetic) on the host cores:
     one 3000 x 3000 pair per call, calls spread over `threads` Python threads
     (ctypes releases the GIL) until `seconds` elapse."""
-    import ctypes as C
     from concurrent.futures import ThreadPoolExecutor
     from oracle import afs_oracle as orc
     L = orc.lib()

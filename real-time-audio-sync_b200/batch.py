@@ -129,6 +129,23 @@ class OtwBatch(object):
         pts = pts.cpu().numpy()[0]
         return st, [[(int(x), int(y)) for x, y in pts[s, : npts[s]]] for s in range(self.n)]
 
+    # ---- checkpoint / resume: every bit of stream state (rings, scalars, paths) lives in the one device block
+    # `self.state`, addressed by offsets only, so a host copy of it is a complete snapshot (the reference keeps the
+    # same information in in-object numpy arrays, otw_eran.py:17-36) ----
+    def _state_meta(self):
+        return {"class": type(self).__name__, "kind": int(self.kind), "c": self.c, "max_run_count": self.max_run_count,
+                "ref_lens": self.ref_lens.tolist(), "state_bytes": self.state_bytes}
+
+    def export_state(self):
+        """Snapshot of all streams (synchronises): {"meta": ..., "state": uint8 CPU tensor}."""
+        return {"meta": self._state_meta(), "state": self.state.cpu().clone()}
+
+    def import_state(self, snap):
+        """Resume from `export_state()` of a batch built with the same references and parameters."""
+        if snap["meta"] != self._state_meta():
+            raise nat.AfsError("snapshot does not match this batch: %r vs %r" % (snap["meta"], self._state_meta()))
+        self.state.copy_(snap["state"].to(self.device))
+
     def _dev_view(self, address, count, dtype):
         """Wrap `count` int32s at a device address inside the state block as a tensor view."""
         base = self.state.data_ptr()
@@ -217,6 +234,12 @@ class WtwBatch(object):
         return self.push_device(torch.from_numpy(c).to(self.device)).cpu().numpy()
 
     _dev_view = OtwBatch._dev_view
+    export_state = OtwBatch.export_state
+    import_state = OtwBatch.import_state
+
+    def _state_meta(self):
+        return {"class": type(self).__name__, "W": self.W, "h": self.h, "ref_lens": self.ref_lens.tolist(),
+                "state_bytes": self.state_bytes}
 
     def positions(self):
         """(n, 3) array of (chroma_ptr, live_ptr, ref_ptr)."""

@@ -172,3 +172,35 @@ def test_fuzz_many_ragged_streams(mods, orc, kind, c, mr):
     for s in range(n):
         assert np.array_equal(got[s], oracles[s].path_array()), (s, ref_lens[s])
     b.close()
+
+
+def test_checkpoint_resume_of_stream_state(mods, orc):
+    """export_state() after 90 frames, import_state() into a fresh batch, continue: identical to an uninterrupted run
+    (paths, positions, stop flags) for OTW and WTW batches; a snapshot of a different configuration is refused."""
+    import torch
+    rng = np.random.default_rng(31)
+    refs = [chroma_like(rng, n) for n in (150, 90, 260)]
+    lives = [warped_copy(rng, r, 220) for r in refs]
+    frames = np.stack([np.stack([lv[:, k] for lv in lives]) for k in range(220)])          # (T, n, 12)
+    B = mods["batch"]
+    for make in (lambda: B.OtwBatch(refs, 20, 3, kind="livenote_v2"), lambda: B.WtwBatch(refs, 16, 8)):
+        full, first = make(), make()
+        step = (lambda b, x: b.step_device(x)[0]) if hasattr(full, "step_device") else (lambda b, x: b.push_device(x))
+        d = torch.from_numpy(frames).cuda()
+        st_full = step(full, d).cpu().numpy()
+        st_a = step(first, d[:90].contiguous()).cpu().numpy()
+        snap = first.export_state()
+        first.close()
+        second = make()
+        second.import_state(snap)
+        st_b = step(second, d[90:].contiguous()).cpu().numpy()
+        assert np.array_equal(np.concatenate([st_a, st_b]), st_full)
+        assert np.array_equal(second.positions(), full.positions())
+        for x, y in zip(second.paths(), full.paths()):
+            assert np.array_equal(x, y)
+        full.close()
+        second.close()
+    other = B.OtwBatch(refs, 21, 3, kind="livenote_v2")
+    with pytest.raises(mods["_native"].AfsError):
+        other.import_state(snap)
+    other.close()
