@@ -786,6 +786,10 @@ def bench_otw(ctx):
         res[kind] = {"p99_ms": p99, "p50_ms": p50, "max_ms": float(lat.max()), "steps": int(len(lat)),
                      "kernel_ms_mean": float(np.mean(dev_ms)), "kernel_ms_p99": float(np.percentile(dev_ms, 99)),
                      "gpu_launches": int(launches),
+                     # per-step latency histogram of this rank (the evidence asked for K5)
+                     "latency_percentiles_ms": {q: float(np.percentile(lat, float(q))) for q in ("10", "50", "90", "99", "99.9")},
+                     "latency_histogram": {"edges_ms": [round(float(e), 4) for e in np.histogram_bin_edges(lat, bins=12)],
+                                           "counts": [int(c) for c in np.histogram(lat, bins=12)[0]]},
                      "stream_steps_per_s": S * world / (float(np.mean(lat)) * 1e-3)}
         if lat_e2e:
             le = np.array(lat_e2e)
