@@ -485,8 +485,8 @@ def bench_dtw(ctx):
                 "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"},
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at exactly this configuration
         # (profiles/ncu_raw_r1d_dtw.csv: 0.944 GB + 3.342 GB); None for any other configuration
-        "traffic": 4.286e9 if (P == 32 and Ln == 20000 and args.dtype == "fp64") else None,
-        "traffic_source": "profiles/ncu_raw_r1d_dtw.csv (ncu --set full, same 32 x 20k x 20k launch)",
+        "traffic": 4.852e9 if (P == 32 and Ln == 20000 and args.dtype == "fp64") else None,
+        "traffic_source": "profiles/ncu_raw_r1j_dtw.csv (ncu --set full, same 32 x 20k x 20k launch: 1.41 GB read + 3.44 GB written)",
         "algorithmic_bytes": alg_bytes,
     }
     cpu = None if args.no_cpu_baseline else cpu_dtw_baseline(seconds=args.cpu_seconds)
@@ -671,9 +671,8 @@ def bench_chroma(ctx):
         "roofline": {"kernel": "chroma_fast_kernel<17>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": gbs / hbm_peak, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                      "bytes_per_frame": CHROMA_BYTES_PER_FRAME,
-                     # ncu (profiles/ncu_raw_r1d_chroma.csv): 346.06 MB of DRAM traffic for a 41 344-frame launch
-                     # = 8370 B/frame (algorithmic 8240), scaled to this launch's frame count
-                     "traffic": 8370.0 * frames, "traffic_source": "profiles/ncu_raw_r1d_chroma.csv, per frame x frames",
+                     # ncu: 346.5 MB of DRAM traffic for a 41 344-frame launch = 8382 B/frame (algorithmic 8240)
+                     "traffic": 8382.0 * frames, "traffic_source": "profiles/ncu_raw_r1m_chroma.csv (346.5 MB for 41 344 frames), per frame x frames",
                      "fp32": {"achieved": tfl, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tfl / fp32_peak,
                               "flop_per_frame": CHROMA_FLOP_PER_FRAME,
                               "peak_source": "derived: %d SMs x 128 lanes x 2 x %.0f MHz" % (n_sm, sm_max)}},
@@ -803,13 +802,15 @@ def bench_otw(ctx):
     o = res["otw"]
     peaks = load_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    # ncu (profiles/ncu_raw_r1d_otw.csv): 831 MB of DRAM traffic for one step of 4096 streams at c = 500 — the
-    # reference and live windows (c x 96 B each) are re-read every step and do not fit L2 for 4096 streams
-    traffic = 831.2e6 * S / 4096.0
-    otw_roof = {"kernel": "otw_step_kernel", "bound": "hbm", "achieved": traffic / (o["kernel_ms_mean"] * 1e-3) / 1e9,
-                "peak": hbm_peak, "unit": "GB/s", "frac": traffic / (o["kernel_ms_mean"] * 1e-3) / 1e9 / hbm_peak,
-                "peak_source": "measured" if "hbm_gbs" in peaks else "fallback", "traffic": traffic,
-                "traffic_source": "profiles/ncu_raw_r1d_otw.csv (one step, 4096 streams), scaled by stream count",
+    # The reference and live windows (c x 96 B each) are re-read every step and do not fit L2 for 4096 streams.
+    # ncu --set full of ONE heavy step (t = 703, all 4096 streams run a row sweep and a column sweep): 1.03 GB read +
+    # 0.06 GB written.  It is set against the live p99 kernel time (the heavy steps), not the mean.
+    traffic = 1.096e9 * S / 4096.0
+    heavy_ms = o["kernel_ms_p99"]
+    otw_roof = {"kernel": "otw_step_kernel", "bound": "hbm", "achieved": traffic / (heavy_ms * 1e-3) / 1e9,
+                "peak": hbm_peak, "unit": "GB/s", "frac": traffic / (heavy_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "measured" if "hbm_gbs" in peaks else "fallback", "traffic": traffic, "kernel_ms": heavy_ms,
+                "traffic_source": "profiles/ncu_raw_r1m_otw.csv (one heavy step, 4096 streams), scaled by stream count; time = live p99 kernel time",
                 "note": "the metric is latency; the step is a chain of <= 5 serial sweeps per stream on top of this traffic"}
     return {
         "metric": "otw_p99_frame_latency_ms", "value": o["p99_ms"], "unit": "ms", "n_gpus": world, "higher_is_better": False,
