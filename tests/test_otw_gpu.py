@@ -204,3 +204,40 @@ def test_checkpoint_resume_of_stream_state(mods, orc):
     with pytest.raises(mods["_native"].AfsError):
         other.import_state(snap)
     other.close()
+
+
+@pytest.mark.parametrize("kind", ["otw", "livenote_v2"])
+def test_full_config_4096_streams_c500_sampled_parity(mods, orc, kind):
+    """BASELINE config[3] at full size — 4096 concurrent streams, c = 500, 3000-frame references, the bench's own data
+    generator — stepped one launch per live frame for 700 frames; the complete paths of 10 sampled streams (first, last,
+    group boundaries, random) are bit-equal to the oracle's."""
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    argv, sys.argv = sys.argv, sys.argv[:1]
+    try:
+        import bench
+    finally:
+        sys.argv = argv
+    S, N, T, c = 4096, 3000, 700, 500
+    ref, frames = bench.synth_streams(torch, S, N, T, 777, "cuda")
+    b = mods["batch"].OtwBatch(ref, c, 3, kind=kind)
+    for k in range(T):
+        b.step_device(frames[k], want_points=False)
+    got = b.paths()
+    pos = b.positions()
+    params = {"c": c, "max_run_count": 3, "search_band_width": c}
+    ocls = orc.OnlineTimeWarping if kind == "otw" else orc.LiveNoteV2
+    rng = np.random.default_rng(3)
+    sample = [0, 6, 7, 13, 4095, 4094] + [int(x) for x in rng.integers(0, S, size=4)]
+    h_ref = ref.cpu().numpy()
+    h_frames = frames.cpu().numpy()
+    for s in sample:
+        o = ocls(np.ascontiguousarray(h_ref[s]), dict(params))
+        for k in range(T):
+            if o.insert(h_frames[k, s]) == "stop":
+                break
+        assert np.array_equal(got[s], o.path_array()), (kind, s)
+        assert (int(pos[s, 0]), int(pos[s, 1])) == (o.t, o.j), (kind, s)
+    b.close()
