@@ -478,8 +478,9 @@ def bench_dtw(ctx):
         "frac": achieved_tflops / pipe_peak_tflops,
         "peak_source": "derived: %d SMs x %d lanes x 2 x %.0f MHz (MEASURED_PEAKS.json has no %s pipe figure)" % (n_sm, lanes, sm_max, args.dtype),
         "flop_per_cell": DTW_FLOP_PER_CELL, "kernel_ms": acc_ms_mean,
-        "practical_ceiling": "tools/ubench_fp64.cu on B200: DFMA with 3 distinct register operands 2.6 cycles per warp instruction per "
-                             "sub-partition (nominal 2.0), DSETP+2xFSEL 4.95 -> ~205 cycles per 128-cell step = ~710 GCUPS (fp64), see DESIGN.md K2",
+        "practical_ceiling": "tools/ubench_split.cu on B200: the step's arithmetic alone (cost FMAs + DP chain + shuffle, no hand-off / TMA / "
+                             "stores) takes 225 cycles per 128-cell step per sub-partition = ~660 GCUPS (fp64); DFMA with 3 distinct register "
+                             "operands costs 2.6 pipe cycles (nominal 2.0), see DESIGN.md K2",
         "hbm": {"achieved": alg_bytes / (acc_ms_mean * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (acc_ms_mean * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"},
