@@ -5,8 +5,9 @@
   python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port on host cores)
 
 Headline metric (BASELINE.json): DTW GCUPS on config[2] — 20k x 20k chroma frames,
-256 pairs sharded over 8 GPUs = 32 pairs per GPU (weak scaling: 32 pairs per rank).
-One "step" = one pass (accumulate K2 + backtrack K3) over the rank's 32 pairs.
+batch of 256 pairs.  The batch fits one GPU (26.5 GB of direction maps), so every GPU runs the configuration in full:
+256 pairs per rank at every N (weak scaling).  One "step" = one pass (accumulate K2 + backtrack K3) over the rank's 256
+pairs.  (`--pairs 32` gives the config's 8-GPU share per GPU: 492 instead of 640 GCUPS per GPU, see DESIGN.md.)
 The same JSON line carries the other two metrics BASELINE.json names as sub-objects
 (`chroma`: frames/s on config[1]; `otw`: p99 per-frame latency on config[3]) when
 those workloads are enabled (--workloads dtw,chroma,otw; default all available).
@@ -27,7 +28,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 DTW_LEN = 20000
-DTW_PAIRS_PER_GPU = 32          # 256 pairs / 8 GPUs (BASELINE.json configs[2])
+DTW_PAIRS_PER_GPU = 256         # BASELINE.json configs[2]: a batch of 256 pairs; it fits one GPU, so each GPU runs it in full
 FP64_LANES_PER_SM = 64          # B200 FP64 FMA lanes per SM
 DTW_FLOP_PER_CELL = 31          # 12 FMA + sub + scale + 3 add + 2 cmp/sel
 
@@ -166,7 +167,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "dtw_gcups", "value": v, "unit": "GCUPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "offline full DTW 20k x 20k chroma frames, 32 pairs per GPU (cfg[2]); CPU arm = bounded sample of 3000x3000 pairs, same arithmetic"},
+        "config": {"workload": "offline full DTW 20k x 20k chroma frames, batch of 256 pairs per GPU (BASELINE cfg[2]); CPU arm = bounded sample of 3000x3000 pairs, same arithmetic"},
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -237,6 +238,7 @@ def main():
     results = {}
     if "dtw" in wl:
         results["dtw"] = bench_dtw(ctx)
+        torch.cuda.empty_cache()          # 80+ GB of plans go back to the driver before the next workload allocates
     if "chroma" in wl:
         results["chroma"] = bench_chroma(ctx)
     if "otw" in wl:
@@ -484,10 +486,11 @@ def bench_dtw(ctx):
         "hbm": {"achieved": alg_bytes / (acc_ms_mean * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (acc_ms_mean * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"},
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at exactly this configuration
-        # (profiles/ncu_raw_r1d_dtw.csv: 0.944 GB + 3.342 GB); None for any other configuration
-        "traffic": 4.852e9 if (P == 32 and Ln == 20000 and args.dtype == "fp64") else None,
-        "traffic_source": "profiles/ncu_raw_r1j_dtw.csv (ncu --set full, same 32 x 20k x 20k launch: 1.41 GB read + 3.44 GB written)",
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at exactly this configuration; None for any other.
+        # 256 pairs: the packed seq_b of all pairs (573 MB) no longer fits L2, so the per-band re-reads of seq_b reach DRAM
+        # (80.7 GB read + 37.3 GB written; 0.76 TB/s = 12 % of the HBM peak, not limiting: see DESIGN.md K2).
+        "traffic": {(256, 20000): 118.05e9, (32, 20000): 4.852e9}.get((P, Ln)) if args.dtype == "fp64" else None,
+        "traffic_source": "profiles/ncu_raw_r1n_dtw.csv (256 pairs) / ncu_raw_r1j_dtw.csv (32 pairs): ncu --set full of the same launch",
         "algorithmic_bytes": alg_bytes,
     }
     cpu = None if args.no_cpu_baseline else cpu_dtw_baseline(seconds=args.cpu_seconds)
@@ -495,7 +498,7 @@ def bench_dtw(ctx):
         "metric": "dtw_gcups", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup_effective, "ms_per_step": step_ms_max, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64" if args.dtype == "fp64" else "f32", "data": "synthetic",
-        "config": {"workload": "offline full DTW %dx%d chroma frames, %d pairs per GPU (BASELINE cfg[2]: 256 pairs over 8 GPUs)" % (Ln, Ln, P),
+        "config": {"workload": "offline full DTW %dx%d chroma frames, batch of %d pairs per GPU (BASELINE cfg[2] in full on every GPU; weak scaling)" % (Ln, Ln, P),
                    "pairs_per_gpu": P, "frames": Ln, "features": 12,
                    "l2": "256 MiB flush between timed steps; per-step working set 3.2 GB direction map > 126 MB L2",
                    "step": "accumulate (K2) + backtrack (K3)", "parallelism": "pairs sharded over ranks, no collective"},
