@@ -39,7 +39,9 @@ typedef enum afs_status {
     AFS_ERR_UNSUPPORTED = -4  /* parameter outside what the kernels implement */
 } afs_status;
 
-typedef enum afs_dtype { AFS_F64 = 0, AFS_F32 = 1 } afs_dtype;
+/* AFS_BF16X3: only as afs_chroma_batch's compute_dtype — the tcgen05 path (DFT as two matrix products, every
+ * operand split into two bf16 terms, fp32 accumulation in TMEM); <= 2e-5 abs on normalised chroma. */
+typedef enum afs_dtype { AFS_F64 = 0, AFS_F32 = 1, AFS_BF16X3 = 2 } afs_dtype;
 
 const char *afs_last_error(void);
 /* "libafsync <version> sm_100a" */
@@ -173,6 +175,11 @@ int afs_chroma_batch(afs_chroma_plan *plan, const float *d_audio, const int64_t 
 int afs_chroma_batch_pcm16(afs_chroma_plan *plan, const int16_t *d_pcm, const int64_t *h_offsets, int n_tracks,
                            int center_pad, int normalize, void *d_out, const int64_t *h_out_offsets,
                            int out_dtype, int compute_dtype, void *stream);
+/* chroma.create_stft (chroma.py:44-65 == wtw.WTW.stft, wtw.py:137-160) on its own: the complex spectrum
+ * np.fft.rfft(frame * np.hanning(4096)) of every frame, [frame][2049] interleaved (re, im) of the compute type
+ * (AFS_F32: complex64, AFS_F64: complex128); frame k of track t is row h_out_offsets[t] + k (NULL = packed). */
+int afs_stft_batch(afs_chroma_plan *plan, const float *d_audio, const int64_t *h_offsets, int n_tracks, int center_pad,
+                   void *d_spec, const int64_t *h_out_offsets, int compute_dtype, void *stream);
 
 /* ===================================================================== WTW
  * Replaces wtw.WTW.insert's window loop (wtw.py:100-128) with get_cost_matrix

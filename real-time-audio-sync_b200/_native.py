@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # AFSYNC_LIB: developer override to time an alternative build of the same ABI (default: the in-tree library)
 LIB_PATH = os.environ.get("AFSYNC_LIB") or os.path.join(_HERE, "libafsync.so")
 
-AFS_F64, AFS_F32 = 0, 1
+AFS_F64, AFS_F32, AFS_BF16X3 = 0, 1, 2
 AFS_OTW, AFS_LIVENOTE_V2, AFS_LIVENOTE_V1 = 0, 1, 2
 AFS_COST_COSINE, AFS_COST_EUCLID = 0, 1
 AFS_STEP_NONE, AFS_STEP_STOP, AFS_STEP_FULL = 0, 1, 2
@@ -60,6 +60,7 @@ _SIGNATURES = {
     "afs_chroma_num_frames": (C.c_int64, [_vp, C.c_int64, C.c_int]),
     "afs_chroma_batch": (C.c_int, [_vp, _vp, _i64p, C.c_int, C.c_int, C.c_int, _vp, _i64p, C.c_int, C.c_int, _vp]),
     "afs_chroma_batch_pcm16": (C.c_int, [_vp, _vp, _i64p, C.c_int, C.c_int, C.c_int, _vp, _i64p, C.c_int, C.c_int, _vp]),
+    "afs_stft_batch": (C.c_int, [_vp, _vp, _i64p, C.c_int, C.c_int, _vp, _i64p, C.c_int, _vp]),
     "afs_wtw_create": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, _i64p, _i64p, C.c_int, C.c_int, C.c_int]),
     "afs_wtw_destroy": (C.c_int, [_vp]),
     "afs_wtw_state_bytes": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),

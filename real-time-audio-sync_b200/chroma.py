@@ -7,11 +7,13 @@ and the L2 normalisation run fused in kernel K1 (csrc/chroma.cu) through
 ``afs_chroma_batch``; WAV decoding stays on the CPU (it only feeds samples).
 
 Differences from the reference, all explicit:
-* ``create_stft`` is not exposed on its own — the spectrum never leaves the SM; use
-  ``wav_samples_to_chroma`` / ``chroma_batch`` (or ``create_chroma(create_stft(wav))``,
-  where ``create_stft`` returns a lazy handle that ``create_chroma`` consumes);
-* arithmetic is float32 by default (<= 1e-6 abs from the float64 reference on real
-  audio); ``compute="fp64"`` runs the same kernel in float64;
+* three arithmetic modes: ``compute="fp32"`` (default) runs the DFT as two matrix products on the
+  tensor cores with bf16x3 split operands and fp32 accumulation (<= 2e-5 abs from the float64
+  reference on normalised chroma); ``"fp32"`` is the CUDA-core FFT kernel in float32 (<= 1e-6);
+  ``"fp64"`` the same kernel in float64 (<= 1e-9);
+* ``create_stft`` returns the complex (2049, M) spectrum like the reference (float64 kernel) wrapped in an
+  array subclass that remembers the samples, so ``create_chroma(create_stft(wav))`` runs the fused path;
+  ``create_chroma`` on any other (2049, M) array applies filterbank + normalisation to that spectrum;
 * ``librosa.load`` is replaced by a WAV reader for 22 050 Hz PCM16 files (no resampler).
 """
 import ctypes as C
@@ -46,6 +48,10 @@ def chroma_filterbank(sr=fs, n_fft=fft_len, n_chroma=12, A440=440.0, ctroct=5.0,
     wts *= np.tile(np.exp(-0.5 * (((bins / n_chroma - ctroct) / octwidth) ** 2)), (n_chroma, 1))
     wts = np.roll(wts, -3 * (n_chroma // 12), axis=0)
     return np.ascontiguousarray(wts[:, : int(1 + n_fft / 2)])
+
+
+_COMPUTE = {"tc": nat.AFS_BF16X3, "bf16x3": nat.AFS_BF16X3, "fp32": nat.AFS_F32, "f32": nat.AFS_F32,
+            "fp64": nat.AFS_F64, "f64": nat.AFS_F64}
 
 
 class ChromaPlan(object):
@@ -92,12 +98,28 @@ class ChromaPlan(object):
             d_out = torch.empty(int(12 * foffs[-1]), dtype=out_dtype, device=d_audio.device)
         oo = None if out_offsets is None else np.ascontiguousarray(out_offsets, dtype=np.int64)
         entry = nat.lib().afs_chroma_batch_pcm16 if d_audio.dtype == torch.int16 else nat.lib().afs_chroma_batch
-        nat.check(entry(
-            self._h, nat.ptr(d_audio), offs.ctypes.data_as(nat._i64p), n, 1 if center else 0, 1 if normalize else 0,
-            nat.ptr(d_out), None if oo is None else oo.ctypes.data_as(nat._i64p),
-            nat.AFS_F64 if d_out.dtype == torch.float64 else nat.AFS_F32,
-            nat.AFS_F64 if compute in ("fp64", "f64") else nat.AFS_F32, nat.stream_ptr()))
+        with torch.cuda.device(d_audio.device):
+            nat.check(entry(
+                self._h, nat.ptr(d_audio), offs.ctypes.data_as(nat._i64p), n, 1 if center else 0, 1 if normalize else 0,
+                nat.ptr(d_out), None if oo is None else oo.ctypes.data_as(nat._i64p),
+                nat.AFS_F64 if d_out.dtype == torch.float64 else nat.AFS_F32, _COMPUTE[compute], nat.stream_ptr()))
         return d_out, foffs
+
+    def stft(self, d_audio, offsets, center=True, compute="fp64"):
+        """create_stft (chroma.py:44-65) for a batch: returns (d_spec, frame_offsets) with d_spec a complex
+        (total_frames, 2049) device tensor (complex128 for compute="fp64", complex64 for "fp32")."""
+        assert d_audio.is_cuda and d_audio.dtype == torch.float32
+        offs = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offs.shape[0] - 1
+        frames = np.array([self.num_frames(offs[k + 1] - offs[k], center) for k in range(n)], dtype=np.int64)
+        foffs = np.concatenate(([0], np.cumsum(frames))).astype(np.int64)
+        f64 = compute in ("fp64", "f64")
+        d_spec = torch.empty((int(foffs[-1]), 1 + self.n_fft // 2), dtype=torch.complex128 if f64 else torch.complex64,
+                             device=d_audio.device)
+        with torch.cuda.device(d_audio.device):
+            nat.check(nat.lib().afs_stft_batch(self._h, nat.ptr(d_audio), offs.ctypes.data_as(nat._i64p), n, 1 if center else 0,
+                                               nat.ptr(d_spec), None, nat.AFS_F64 if f64 else nat.AFS_F32, nat.stream_ptr()))
+        return d_spec, foffs
 
 
 _default_plan = None
@@ -178,24 +200,50 @@ def wav_to_chroma_col(wav_buf, compute="fp32"):
     return chroma_batch([np.asarray(wav_buf)], center=False, compute=compute)[0][:, 0]
 
 
-class _LazyStft(object):
-    """What create_stft returns here: the samples, to be consumed by create_chroma
-    (the spectrum itself is never materialised on the GPU path)."""
+class Stft(np.ndarray):
+    """What create_stft returns: the reference's complex (2049, M) spectrum, plus the samples it came from so that
+    create_chroma can run the fused path instead of re-reading the spectrum."""
 
-    def __init__(self, wav):
-        self.wav = np.asarray(wav)
+    def __new__(cls, spectrum, wav):
+        obj = np.asarray(spectrum).view(cls)
+        obj.wav = wav
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.wav = getattr(obj, "wav", None) if obj is not None and getattr(obj, "shape", None) == self.shape else None
 
 
-def create_stft(wav):
-    """chroma.py:44-65 (lazy: see module docstring)."""
-    return _LazyStft(wav)
+def create_stft(wav, compute="fp64"):
+    """chroma.py:44-65: zero-pad fft_len/2 on the left, frames of fft_len at hop_size, Hann window, rfft.
+    Returns the complex (1 + fft_len/2, num_hops) array (complex128), computed by the float64 kernel."""
+    plan = default_plan()
+    x = np.ascontiguousarray(np.asarray(wav), dtype=np.float32)
+    pad = (len(x) + 3) // 4 * 4
+    flat = np.zeros(pad, dtype=np.float32)
+    flat[: len(x)] = x
+    d_audio = torch.from_numpy(flat).to(plan.device)
+    d_spec, foffs = plan.stft(d_audio, np.array([0, len(x)], dtype=np.int64), center=True, compute=compute)
+    spec = d_spec.cpu().numpy().astype(np.complex128, copy=False).T
+    return Stft(np.ascontiguousarray(spec), x)
 
 
 def create_chroma(ft, normalize=True):
-    """chroma.py:67-75 for the handle returned by create_stft."""
-    if not isinstance(ft, _LazyStft):
-        raise nat.AfsError("create_chroma expects the handle returned by create_stft (spectra are not materialised)")
-    return wav_samples_to_chroma(ft.wav, normalize=normalize)
+    """chroma.py:67-75: |ft|^2 through the (12, 2049) filterbank, L2-normalised per frame.  A spectrum that
+    came from create_stft is recomputed from its samples by the fused kernel; any other (2049, M) complex
+    array goes through the filterbank + normalisation on the device."""
+    if isinstance(ft, Stft) and ft.wav is not None:
+        return wav_samples_to_chroma(ft.wav, normalize=normalize)
+    plan = default_plan()
+    spec = torch.from_numpy(np.ascontiguousarray(np.asarray(ft), dtype=np.complex128)).to(plan.device)
+    assert spec.dim() == 2 and spec.shape[0] == 1 + fft_len // 2, "expected a (2049, M) spectrum"
+    power = spec.real ** 2 + spec.imag ** 2                                    # chroma.py:68
+    fbank = torch.from_numpy(plan.filterbank).to(plan.device)
+    raw = fbank @ power                                                        # chroma.py:70
+    if normalize:
+        length = torch.sqrt((raw * raw).sum(dim=0, keepdim=True))             # chroma.py:74, librosa.util.normalize(norm=2)
+        length = torch.where(length < np.finfo(np.float64).tiny, torch.ones_like(length), length)
+        raw = raw / length
+    return raw.cpu().numpy()
 
 
 def chroma_to_diff(chroma):

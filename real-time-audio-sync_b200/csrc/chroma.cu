@@ -19,7 +19,10 @@
 #include <cmath>
 #include <vector>
 
+#include <mutex>
+
 #include "afs_common.cuh"
+#include "chroma_tc.cuh"
 
 namespace {
 
@@ -104,17 +107,6 @@ struct ChromaTables {
     const T *fb;            // [2049][12]
 };
 
-struct ChromaBatch {
-    const void *audio;           // float32 samples, or int16 PCM (pcm16 = 1: sample = value / 32768, librosa.load's scaling)
-    int pcm16;
-    const int64_t *sample_off;   // n_tracks + 1
-    const int64_t *frame_off;    // n_tracks + 1 (prefix of frames per track)
-    const int64_t *out_off;      // n_tracks (frames), output placement
-    int n_tracks;
-    int64_t total_frames;
-    int hop, center_pad, normalize, out_f64;
-    void *out;
-};
 
 // sample s of a track that starts at element s_begin, as librosa.load would deliver it (float32)
 __device__ __forceinline__ float load_sample(const ChromaBatch &bt, int64_t idx)
@@ -195,6 +187,7 @@ __global__ void __launch_bounds__(kThreads) chroma_kernel(const ChromaTables<T> 
         }
         __syncthreads();
         // ---- untangle + power + filterbank ----
+        Cx<T> *spec = bt.stft_out ? static_cast<Cx<T> *>(bt.stft_out) + (bt.out_off[track] + m_idx) * kBins : nullptr;
         T acc[kChroma];
 #pragma unroll
         for (int c = 0; c < kChroma; c++) acc[c] = (T)0;
@@ -213,6 +206,7 @@ __global__ void __launch_bounds__(kThreads) chroma_kernel(const ChromaTables<T> 
                 add_bin(2048, xn * xn);
                 const Cx<T> zq = sA[1024];                        // X[1024] = conj(Z[1024])
                 add_bin(1024, zq.x * zq.x + zq.y * zq.y);
+                if (spec) { spec[0] = Cx<T>{x0, (T)0}; spec[2048] = Cx<T>{xn, (T)0}; spec[1024] = Cx<T>{zq.x, -zq.y}; }
             } else {
                 const Cx<T> zk = sA[k], zn = sA[kNc - k];
                 const Cx<T> e = {(T)0.5 * (zk.x + zn.x), (T)0.5 * (zk.y - zn.y)};     // (Zk + conj Zn)/2
@@ -222,6 +216,7 @@ __global__ void __launch_bounds__(kThreads) chroma_kernel(const ChromaTables<T> 
                 const Cx<T> xa = cadd(e, o), xb = csub(e, o);                         // X[k], conj X[2048-k]
                 add_bin(k, xa.x * xa.x + xa.y * xa.y);                                // chroma.py:68 abs(ft)**2
                 add_bin(kNc - k, xb.x * xb.x + xb.y * xb.y);
+                if (spec) { spec[k] = xa; spec[kNc - k] = Cx<T>{xb.x, -xb.y}; }       // chroma.py:63 np.fft.rfft
             }
         }
         // ---- block reduction of the 12 partial sums (chroma.py:70 np.dot(chromafb, spec)) ----
@@ -252,7 +247,7 @@ __global__ void __launch_bounds__(kThreads) chroma_kernel(const ChromaTables<T> 
                 if (len < tiny) len = (T)1;
                 val = raw / len;
             }
-            if (lane < kChroma) {
+            if (lane < kChroma && bt.out) {
                 const int64_t o = kChroma * bt.out_off[track] + (int64_t)lane * frames_k + m_idx;
                 if (bt.out_f64) static_cast<double *>(bt.out)[o] = (double)val;
                 else static_cast<float *>(bt.out)[o] = (float)val;
@@ -556,9 +551,13 @@ struct afs_chroma_plan {
     Cx<float> *f_tw2048 = nullptr, *f_tw4096 = nullptr;
     double *d_hann = nullptr, *d_fb = nullptr;
     Cx<double> *d_tw2048 = nullptr, *d_tw4096 = nullptr;
-    int64_t *d_meta = nullptr;     // sample_off | frame_off | out_off
-    int meta_cap = 0;
-    std::vector<int64_t> h_meta;   // host copy of the per-batch offsets
+    // tensor-core pipeline (csrc/chroma_tc.cu): tables + the chunk scratch for the power spectrum
+    afs_chroma_tc *tc = nullptr;
+    // launches of one plan are serialised across streams: the tensor path owns one scratch buffer per plan
+    std::mutex mu;
+    cudaEvent_t last_done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_last = false;
     // fast-path tables (class-sorted sparse filterbank); fast_ok == false -> generic kernel only
     bool fast_ok = false;
     int bpt = 0, nd = 0;
@@ -697,6 +696,10 @@ int afs_chroma_plan_create(afs_chroma_plan **out, const double *h_filterbank, in
         afs_chroma_plan_destroy(pl);
         return rc2;
     }
+    if (int rc3 = chroma_tc_create(&pl->tc, fb, hann)) {
+        afs_chroma_plan_destroy(pl);
+        return rc3;
+    }
     *out = pl;
     return AFS_OK;
 }
@@ -706,7 +709,8 @@ int afs_chroma_plan_destroy(afs_chroma_plan *pl)
     if (!pl) return AFS_OK;
     cudaFree(pl->f_hann); cudaFree(pl->f_fb); cudaFree(pl->f_tw2048); cudaFree(pl->f_tw4096);
     cudaFree(pl->d_hann); cudaFree(pl->d_fb); cudaFree(pl->d_tw2048); cudaFree(pl->d_tw4096);
-    cudaFree(pl->d_meta);
+    chroma_tc_destroy(pl->tc);
+    if (pl->last_done) cudaEventDestroy(pl->last_done);
     cudaFree(pl->f_wsp); cudaFree(pl->f_wdense); cudaFree(pl->f_tw1); cudaFree(pl->u_paddr); cudaFree(pl->u_kdense); cudaFree(pl->i_cls);
     delete pl;
     return AFS_OK;
@@ -738,56 +742,17 @@ static int launch_chroma(const ChromaTables<T> &tb, const ChromaBatch &bt, cudaS
     return AFS_OK;
 }
 
-static int chroma_batch_impl(afs_chroma_plan *pl, const void *d_audio, int pcm16, const int64_t *h_offsets, int n_tracks,
-                             int center_pad, int normalize, void *d_out, const int64_t *h_out_offsets, int out_dtype,
-                             int compute_dtype, void *stream)
+static int chroma_launch(afs_chroma_plan *pl, ChromaBatch &bt, int compute_dtype, cudaStream_t st)
 {
-    if (!pl || !d_audio || !h_offsets || !d_out || n_tracks <= 0)
-        return afs::fail(AFS_ERR_INVALID, "afs_chroma_batch: null argument or n_tracks <= 0");
-    if ((out_dtype != AFS_F32 && out_dtype != AFS_F64) || (compute_dtype != AFS_F32 && compute_dtype != AFS_F64))
-        return afs::fail(AFS_ERR_INVALID, "afs_chroma_batch: bad dtype");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // the host copy lives in the plan: it must stay valid until the async copy below has been staged,
-    // whatever kind of host memory the runtime takes it for (one batch in flight per plan)
-    std::vector<int64_t> &meta = pl->h_meta;
-    meta.assign((size_t)3 * n_tracks + 2, 0);
-    int64_t *s_off = meta.data(), *f_off = s_off + n_tracks + 1, *o_off = f_off + n_tracks + 1;
-    f_off[0] = 0;
-    for (int k = 0; k < n_tracks; k++) {
-        if (h_offsets[k + 1] < h_offsets[k]) return afs::fail(AFS_ERR_INVALID, "afs_chroma_batch: offsets must be non-decreasing");
-        if (h_offsets[k] & 1) return afs::fail(AFS_ERR_INVALID, "afs_chroma_batch: track offsets must be even (8-byte aligned samples)");
-        s_off[k] = h_offsets[k];
-        f_off[k + 1] = f_off[k] + afs_chroma_num_frames(pl, h_offsets[k + 1] - h_offsets[k], center_pad);
-        o_off[k] = h_out_offsets ? h_out_offsets[k] : f_off[k];
+    if (compute_dtype == AFS_BF16X3) {
+        if (!pl->tc) return afs::fail(AFS_ERR_UNSUPPORTED, "afs_chroma_batch: the tensor-core path is not available for this plan");
+        return chroma_tc_run(pl->tc, bt, st);
     }
-    s_off[n_tracks] = h_offsets[n_tracks];
-    const int64_t total = f_off[n_tracks];
-    if (total == 0) return AFS_OK;
-    if (pl->meta_cap < (int)meta.size()) {
-        cudaFree(pl->d_meta);
-        pl->d_meta = nullptr;
-        AFS_CUDA(cudaMalloc(&pl->d_meta, sizeof(int64_t) * meta.size()));
-        pl->meta_cap = (int)meta.size();
-    }
-    AFS_CUDA(cudaMemcpyAsync(pl->d_meta, meta.data(), sizeof(int64_t) * meta.size(), cudaMemcpyHostToDevice, st));
-    ChromaBatch bt;
-    bt.audio = d_audio;
-    bt.pcm16 = pcm16;
-    bt.sample_off = pl->d_meta;
-    bt.frame_off = pl->d_meta + n_tracks + 1;
-    bt.out_off = pl->d_meta + 2 * (n_tracks + 1);
-    bt.n_tracks = n_tracks;
-    bt.total_frames = total;
-    bt.hop = pl->hop;
-    bt.center_pad = center_pad;
-    bt.normalize = normalize;
-    bt.out_f64 = out_dtype == AFS_F64;
-    bt.out = d_out;
-    if (compute_dtype == AFS_F32 && pl->fast_ok) {
+    if (compute_dtype == AFS_F32 && pl->fast_ok && !bt.stft_out) {
         ChromaFastTables ft{pl->f_hann, reinterpret_cast<const float2 *>(pl->f_tw2048), reinterpret_cast<const float2 *>(pl->f_tw4096),
                             reinterpret_cast<const float2 *>(pl->f_tw1), pl->f_wsp, pl->u_paddr, pl->i_cls, pl->f_wdense, pl->u_kdense, pl->bpt, pl->nd};
-        auto kern = pcm16 ? (pl->bpt == 17 ? chroma_fast_kernel<17, true> : chroma_fast_kernel<0, true>)
-                          : (pl->bpt == 17 ? chroma_fast_kernel<17, false> : chroma_fast_kernel<0, false>);
+        auto kern = bt.pcm16 ? (pl->bpt == 17 ? chroma_fast_kernel<17, true> : chroma_fast_kernel<0, true>)
+                             : (pl->bpt == 17 ? chroma_fast_kernel<17, false> : chroma_fast_kernel<0, false>);
         int occ = 0;
         AFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 0));
         if (occ < 1) return afs::fail(AFS_ERR_CUDA, "chroma fast kernel does not fit on an SM");
@@ -806,6 +771,66 @@ static int chroma_batch_impl(afs_chroma_plan *pl, const void *d_audio, int pcm16
     return launch_chroma<double>(tb, bt, st);
 }
 
+static int chroma_batch_impl(afs_chroma_plan *pl, const void *d_audio, int pcm16, const int64_t *h_offsets, int n_tracks,
+                             int center_pad, int normalize, void *d_out, const int64_t *h_out_offsets, int out_dtype,
+                             int compute_dtype, void *stream, void *d_stft = nullptr)
+{
+    if (!pl || !d_audio || !h_offsets || (!d_out && !d_stft) || n_tracks <= 0)
+        return afs::fail(AFS_ERR_INVALID, "afs_chroma_batch: null argument or n_tracks <= 0");
+    if ((out_dtype != AFS_F32 && out_dtype != AFS_F64) ||
+        (compute_dtype != AFS_F32 && compute_dtype != AFS_F64 && compute_dtype != AFS_BF16X3))
+        return afs::fail(AFS_ERR_INVALID, "afs_chroma_batch: bad dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // per-call offsets: sample_off | frame_off | out_off.  The device copy is allocated and freed in stream order,
+    // so concurrent calls (other streams, other threads) never share it.
+    std::vector<int64_t> meta((size_t)3 * n_tracks + 2, 0);
+    int64_t *s_off = meta.data(), *f_off = s_off + n_tracks + 1, *o_off = f_off + n_tracks + 1;
+    f_off[0] = 0;
+    for (int k = 0; k < n_tracks; k++) {
+        if (h_offsets[k + 1] < h_offsets[k]) return afs::fail(AFS_ERR_INVALID, "afs_chroma_batch: offsets must be non-decreasing");
+        if (h_offsets[k] & 1) return afs::fail(AFS_ERR_INVALID, "afs_chroma_batch: track offsets must be even (8-byte aligned samples)");
+        s_off[k] = h_offsets[k];
+        f_off[k + 1] = f_off[k] + afs_chroma_num_frames(pl, h_offsets[k + 1] - h_offsets[k], center_pad);
+        o_off[k] = h_out_offsets ? h_out_offsets[k] : f_off[k];
+    }
+    s_off[n_tracks] = h_offsets[n_tracks];
+    const int64_t total = f_off[n_tracks];
+    if (total == 0) return AFS_OK;
+    std::lock_guard<std::mutex> lock(pl->mu);
+    if (pl->has_last && pl->last_stream != st) AFS_CUDA(cudaStreamWaitEvent(st, pl->last_done, 0));
+    int64_t *d_meta = nullptr;
+    AFS_CUDA(cudaMallocAsync(&d_meta, sizeof(int64_t) * meta.size(), st));
+    // pageable source: the runtime stages it before cudaMemcpyAsync returns, so `meta` may go out of scope
+    cudaError_t ce = cudaMemcpyAsync(d_meta, meta.data(), sizeof(int64_t) * meta.size(), cudaMemcpyHostToDevice, st);
+    if (ce != cudaSuccess) {
+        cudaFreeAsync(d_meta, st);
+        return afs::fail(AFS_ERR_CUDA, "afs_chroma_batch: %s", cudaGetErrorString(ce));
+    }
+    ChromaBatch bt;
+    bt.audio = d_audio;
+    bt.pcm16 = pcm16;
+    bt.sample_off = d_meta;
+    bt.frame_off = d_meta + n_tracks + 1;
+    bt.out_off = d_meta + 2 * (n_tracks + 1);
+    bt.n_tracks = n_tracks;
+    bt.total_frames = total;
+    bt.hop = pl->hop;
+    bt.center_pad = center_pad;
+    bt.normalize = normalize;
+    bt.out_f64 = out_dtype == AFS_F64;
+    bt.out = d_out;
+    bt.stft_out = d_stft;
+    const int rc = chroma_launch(pl, bt, compute_dtype, st);
+    cudaFreeAsync(d_meta, st);
+    if (rc == AFS_OK) {
+        if (!pl->last_done) AFS_CUDA(cudaEventCreateWithFlags(&pl->last_done, cudaEventDisableTiming));
+        AFS_CUDA(cudaEventRecord(pl->last_done, st));
+        pl->last_stream = st;
+        pl->has_last = true;
+    }
+    return rc;
+}
+
 extern "C" int afs_chroma_batch(afs_chroma_plan *pl, const float *d_audio, const int64_t *h_offsets, int n_tracks,
                                 int center_pad, int normalize, void *d_out, const int64_t *h_out_offsets, int out_dtype,
                                 int compute_dtype, void *stream)
@@ -820,4 +845,15 @@ extern "C" int afs_chroma_batch_pcm16(afs_chroma_plan *pl, const int16_t *d_pcm,
 {
     return chroma_batch_impl(pl, d_pcm, 1, h_offsets, n_tracks, center_pad, normalize, d_out, h_out_offsets, out_dtype,
                              compute_dtype, stream);
+}
+
+// create_stft (chroma.py:44-65): the complex spectrum itself, [frame][2049] interleaved (re, im) of the compute type
+// (complex64 for AFS_F32, complex128 for AFS_F64); frame k of track t sits at row h_out_offsets[t] + k.
+extern "C" int afs_stft_batch(afs_chroma_plan *pl, const float *d_audio, const int64_t *h_offsets, int n_tracks, int center_pad,
+                              void *d_spec, const int64_t *h_out_offsets, int compute_dtype, void *stream)
+{
+    if (!d_spec) return afs::fail(AFS_ERR_INVALID, "afs_stft_batch: null output");
+    if (compute_dtype != AFS_F32 && compute_dtype != AFS_F64) return afs::fail(AFS_ERR_INVALID, "afs_stft_batch: compute_dtype must be AFS_F32 or AFS_F64");
+    return chroma_batch_impl(pl, d_audio, 0, h_offsets, n_tracks, center_pad, 0, nullptr, h_out_offsets, AFS_F32, compute_dtype, stream,
+                             d_spec);
 }

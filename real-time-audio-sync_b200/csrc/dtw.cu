@@ -833,6 +833,12 @@ int afs_dtw_plan_path_layout(const afs_dtw_plan *pl, int pair, int64_t *offset, 
 
 }  // extern "C"
 
+static uint32_t next_launch_epoch()
+{
+    static std::atomic<uint32_t> g_epoch{0};
+    return g_epoch.fetch_add(1u) % 250u + 1u;
+}
+
 template <typename T>
 static int launch_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b, void *ws, double *d_acc_end,
                              void *dense_cost, void *dense_acc, cudaStream_t st, const double *leftb = nullptr,
@@ -849,16 +855,15 @@ static int launch_accumulate(afs_dtw_plan *pl, const void *d_a, const void *d_b,
     args.brow = reinterpret_cast<uint4 *>(base + pl->dir_bytes);
     args.bt = reinterpret_cast<T *>(base + pl->dir_bytes + pl->brow_bytes);
     args.ticket = reinterpret_cast<int *>(base + pl->dir_bytes + pl->brow_bytes + pl->bt_bytes);
-    if (pl->last_ws != ws) {
-        // first use of this workspace: no stale bytes may look like a valid hand-off record
-        AFS_CUDA(cudaMemsetAsync(args.brow, 0, pl->brow_bytes, st));
-        pl->last_ws = ws;
-    }
-    // the epoch that tags this launch's hand-off records comes from one process-wide counter, so that launches of
-    // different plans that were (against the header's advice) pointed at the same workspace cannot validate each
-    // other's stale records
-    static std::atomic<uint32_t> g_epoch{0};
-    pl->epoch = g_epoch.fetch_add(1u) % 250u + 1u;
+    // Every launch starts from a hand-off area without valid records: the tags only carry an 8-bit launch epoch, so
+    // a relaunch of this plan after exactly 250 k launches elsewhere in the process would otherwise meet records of
+    // its own previous launch that carry the tags it waits for.  The clear costs microseconds (2 rows of 16-byte
+    // records per pair) against a launch of milliseconds.
+    AFS_CUDA(cudaMemsetAsync(args.brow, 0, pl->brow_bytes, st));
+    pl->last_ws = ws;
+    // the epoch still separates launches of different plans that were (against the header's advice) pointed at the
+    // same workspace while both are in flight; one counter for the whole process (fp32 and fp64 plans alike)
+    pl->epoch = next_launch_epoch();
     args.epoch = pl->epoch;
     args.acc_end = d_acc_end;
     args.dense_cost = static_cast<T *>(dense_cost);
