@@ -40,24 +40,54 @@ constexpr int kBins = 2049;
 constexpr int kChroma = 12;
 
 // ---------------- kernel A geometry ----------------
-constexpr int kThreadsA = 512;                 // two pipelines of 256
+// Warp-specialised, one CTA per SM, persistent over groups of 4 frames (two stage-1 tiles of 2 frames each):
+//   warps  0..7   C   convert:   staged audio -> x window -> bf16 hi/lo -> A operand of stage 1, written straight into TMEM
+//   warps  8..15  E1  epilogue 1: D1 (TMEM) -> twiddle -> bf16 hi/lo -> Y' (shared memory, B operand of stage 2)
+//   warps 16..23  E2  epilogue 2: D2 (TMEM) -> |X|^2 -> bf16 hi/lo planes of the power spectrum (global scratch, L2)
+//   warp  24      M   one thread issues every tcgen05.mma; completion is tracked with tcgen05.commit -> mbarrier
+//   warps 25, 26  L   loaders: TMA bulk copies (cp.async.bulk) of the audio into a shared-memory ring; issuing a copy or an
+//                     mbarrier transaction costs a warp 100-200 cycles, so two warps take alternate slots
+// The roles only meet through mbarriers, so while the tensor pipe works on one tile the converters are two tiles
+// ahead and the two epilogues drain the previous results.
+constexpr int kWarpsC = 8, kWarpsE1 = 8, kWarpsE2 = 8;
+constexpr int kWarpsL = 2;
+constexpr int kThreadsA = 32 * (kWarpsC + kWarpsE1 + kWarpsE2 + 1 + kWarpsL);      // 864: + M + L
 constexpr int kRowsPerFrame = 36;              // 33 k1 rows + 3 pad rows (N of stage 2 must be a multiple of 16)
 constexpr int kN1 = 64;                        // stage-1 N: 64 real outputs
 constexpr int kN2 = 4 * kRowsPerFrame;         // stage-2 N: 144
 constexpr int kPlaneWords = 9 * 128;           // power spectrum: 9 words per lane per frame and plane (2 bf16 each)
 constexpr uint32_t kFPlane = 64 * 128;         // F^T image, one plane (hi or lo)
-constexpr uint32_t kA1Plane = 128 * 128;       // stage-1 A operand, one plane
 constexpr uint32_t kYBlk = kN2 * 128;          // stage-2 B operand: one 64-element K block of one plane
 constexpr uint32_t kYPlane = 2 * kYBlk;        // K = 128
-constexpr uint32_t kPipeBytes = 2 * kA1Plane + 2 * kYPlane;
-constexpr uint32_t kSmemA = 2 * kFPlane + 2 * kPipeBytes;        // 229 376 B
-// TMEM columns: G_hi [0,64) | G_lo [64,128) | pipeline 0 accumulators [128,272) | pipeline 1 [272,416)
-constexpr uint32_t kColGhi = 0, kColGlo = 64, kColD0 = 128, kColDStride = kN2;
+constexpr uint32_t kYBuf = 2 * kYPlane;        // hi | lo
+constexpr uint32_t kOffF = 0, kOffY = kOffF + 2 * kFPlane, kOffWin = kOffY + 2 * kYBuf;
+// Audio ring.  A slot holds the samples one half (16 of 32 n1-rows per half frame) of a tile needs, as three pieces of
+// 1024 samples: [first half of frame 0 | second half of frame 0 = first half of frame 1 | second half of frame 1] —
+// consecutive frames of a track overlap by one hop, so the middle piece serves both.  The memory system answers a
+// bulk copy after ~1.6 us, so the ring has to hold ~50 KB per SM in flight to stream at the rate the tensor pipe
+// consumes; that is why G lives in TMEM and the stage-1 A operand is single-buffered.  The window table holds the
+// first half of the (symmetric) Hann window.
+constexpr int kRingSlots = 4;                  // power of two
+constexpr uint32_t kPieceBytes = 1024 * 4, kSlotBytes = 3 * kPieceBytes;
+constexpr uint32_t kOffRing = kOffWin + kNfft * 4;      // window: w[n] for n < 2048, then w[2047 - m] = w[2048 + m] for m < 2048
+constexpr uint32_t kSmemA = kOffRing + kRingSlots * kSlotBytes;          // 229 376 B
+// TMEM columns: G_hi [0,64) | G_lo [64,128) | A1 hi [128,160) lo [160,192) | D1[s] [192 + 64 s, +64) | D2 [320, 464)
+constexpr uint32_t kColGhi = 0, kColGlo = 64, kColA1 = 128, kColD1 = 192, kColD2 = 320;
+// mbarriers
+enum { kBarA1Full = 0, kBarM1Done = 1, kBarD1Free = 3, kBarYFull = 5, kBarM2Done = 7, kBarD2Free = 9, kBarRingFull = 10,
+       kBarRingEmpty = 10 + kRingSlots, kNumBars = 10 + 2 * kRingSlots };
+
+// what the loader tells the converters about a ring slot
+struct SlotInfo {
+    long long base1;    // frame 1 of the tile: element index of its sample 0, and the samples that exist
+    int lo1, hi1;
+    int shared;         // 1: frame 1 starts one hop after frame 0 in the same track (the middle piece serves both)
+    int pad;
+};
 
 struct FrameMeta {
     long long base;     // element index of the frame's sample 0 in the audio array (may point before the track)
     int lo, hi;         // samples lo <= n < hi of the frame exist, the rest is the reference's zero padding
-    int valid;          // frame index inside the chunk
 };
 
 struct SpectrumArgs {
@@ -71,9 +101,9 @@ struct SpectrumArgs {
     const float2 *tw;                          // [33][64]: W4096^(k1 n2) = (cos, -sin)
     const float *hann;                         // 4096
     uint32_t *p_hi, *p_lo;                     // [frame - frame_begin][kPlaneWords]
+    long long *trace;                          // optional (AFS_CHROMA_TC_TRACE): [block][warp][kTraceLen] clock64 stamps
 };
-
-__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+constexpr int kTraceLen = 256;
 
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
 {
@@ -83,67 +113,119 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
                  : "memory");
 }
 
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+__device__ __forceinline__ float ldg_stream(const float *p)
 {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+    float v;
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream(const short *p)
+{
+    short v;
+    asm volatile("ld.global.L1::no_allocate.s16 %0, [%1];" : "=h"(v) : "l"(p));
+    return (float)v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+// mbarrier wait with a long suspend-time hint: the warp sleeps in hardware until the phase completes instead of
+// re-issuing try_wait every few hundred cycles (a third of all issued instructions in the first profile were such spins)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(afs::smem_addr(bar)), "r"(parity), "r"(1000000u)
+                     : "memory");
+    } while (!done);
+}
+// keep the computation of v before whatever volatile operation follows (the scheduler otherwise sinks it behind the wait)
+__device__ __forceinline__ void pin16(uint32_t (&v)[16])
+{
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                 "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(afs::smem_addr(bar)) : "memory");
 }
 
-// where the frame `f` (global numbering) lives; `track` is a cursor that only moves forward
-__device__ __forceinline__ FrameMeta locate_frame(const SpectrumArgs &a, int64_t f, int &track)
+// Where the frame `f` (global numbering) lives.  The cursor keeps the current track's offsets in registers, so the
+// common case (next frame, same track) touches no memory; frames only move forward.
+struct TrackCursor {
+    int track = -1;
+    int64_t f_begin = 0, f_end = 0, s_begin = 0, n_samp = 0;
+};
+__device__ __forceinline__ FrameMeta locate_frame(const SpectrumArgs &a, int64_t f, TrackCursor &c)
 {
     FrameMeta m;
-    m.base = 0; m.lo = 0; m.hi = 0; m.valid = 0;
+    m.base = 0; m.lo = 0; m.hi = 0;
     if (f >= a.frame_end) return m;
-    while (track + 1 < a.n_tracks && a.frame_off[track + 1] <= f) track++;
-    const int64_t s_begin = a.sample_off[track];
-    const int64_t n_samp = a.sample_off[track + 1] - s_begin;
-    const int64_t start = (f - a.frame_off[track]) * a.hop - (a.center_pad ? kNfft / 2 : 0);     // chroma.py:49 left zero pad
-    m.base = s_begin + start;
+    if (c.track < 0 || f >= c.f_end) {
+        int t = c.track < 0 ? 0 : c.track;
+        while (t + 1 < a.n_tracks && __ldg(a.frame_off + t + 1) <= f) t++;
+        c.track = t;
+        c.f_begin = __ldg(a.frame_off + t);
+        c.f_end = __ldg(a.frame_off + t + 1);
+        c.s_begin = __ldg(a.sample_off + t);
+        c.n_samp = __ldg(a.sample_off + t + 1) - c.s_begin;
+    }
+    const int64_t start = (f - c.f_begin) * a.hop - (a.center_pad ? kNfft / 2 : 0);     // chroma.py:49 left zero pad
+    m.base = c.s_begin + start;
     m.lo = start < 0 ? (int)(-start) : 0;
-    const int64_t hi = n_samp - start;
+    const int64_t hi = c.n_samp - start;
     m.hi = hi > kNfft ? kNfft : (hi < 0 ? 0 : (int)hi);
-    m.valid = 1;
     return m;
 }
 
-template <bool PCM16>
+template <bool PCM16, bool TRACE>
 __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const SpectrumArgs args)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t s_tmem;
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ FrameMeta s_meta[2][2][4];          // [pipeline][parity][frame of the group]
+    __shared__ __align__(8) uint64_t s_bar[kNumBars];
+    __shared__ __align__(16) SlotInfo s_slot[kRingSlots];
 
-    const int tid = threadIdx.x;
-    const int pipe = tid >> 8, t = tid & 255;
-    const int wg = t >> 7, ln = t & 127;           // ln = TMEM lane = row of the 128-row tiles
-    const int n2 = ln & 63, fp = ln >> 6;          // stage 1: row = (frame of the pair, n2)
-    const uint32_t lane_base = (uint32_t)(ln & ~31) << 16;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t s_base = afs::smem_addr(smem);
 
-    const uint32_t s_f = afs::smem_addr(smem);
-    const uint32_t s_pipe = s_f + 2 * kFPlane + pipe * kPipeBytes;
-    const uint32_t s_a1_hi = s_pipe, s_a1_lo = s_pipe + kA1Plane;
-    const uint32_t s_y_hi = s_pipe + 2 * kA1Plane, s_y_lo = s_y_hi + kYPlane;
-
-    // ---- one-time setup: F^T images, zeroed Y' tiles (pad rows stay zero), barriers, TMEM, G -> TMEM ----
+    // ---- one-time setup: operand images, zeroed Y' tiles (pad rows stay zero), window, barriers, TMEM, G_hi -> TMEM ----
     {
-        uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        for (int i = tid; i < (int)(2 * kFPlane / 16); i += kThreadsA) dst[i] = args.f_img[i];
-        uint4 *y0 = reinterpret_cast<uint4 *>(smem + 2 * kFPlane);
-        for (int i = tid; i < (int)(2 * kPipeBytes / 16); i += kThreadsA) y0[i] = make_uint4(0, 0, 0, 0);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem + kOffF);
+        for (int i = tid; i < (int)(2 * kFPlane / 16); i += kThreadsA) dst[i] = __ldg(args.f_img + i);
+        uint4 *y0 = reinterpret_cast<uint4 *>(smem + kOffY);
+        for (int i = tid; i < (int)(2 * kYBuf / 16); i += kThreadsA) y0[i] = make_uint4(0, 0, 0, 0);
+        float *w = reinterpret_cast<float *>(smem + kOffWin);
+        // PCM16: librosa.load's 1/32768 scaling (a power of two) rides on the window
+        for (int i = tid; i < kNfft; i += kThreadsA) {
+            // np.hanning is symmetric, w[n] = w[4095 - n]: the second half is stored as the mirror of the first
+            const int n = i < kNfft / 2 ? i : kNfft - 1 - i;
+            w[i] = __ldg(args.hann + n) * (PCM16 ? (1.0f / 32768.0f) : 1.0f);
+        }
     }
     if (tid == 0) {
-        afs::mbar_init(&s_bar[0], 1);
-        afs::mbar_init(&s_bar[1], 1);
+        afs::mbar_init(&s_bar[kBarA1Full], kWarpsC);
+        for (int s = 0; s < 2; s++) {
+            afs::mbar_init(&s_bar[kBarM1Done + s], 1);
+            afs::mbar_init(&s_bar[kBarD1Free + s], kWarpsE1);
+            afs::mbar_init(&s_bar[kBarYFull + s], 2 * kWarpsE1);
+            afs::mbar_init(&s_bar[kBarM2Done + s], 1);
+        }
+        afs::mbar_init(&s_bar[kBarD2Free], kWarpsE2);
+        for (int r = 0; r < kRingSlots; r++) {
+            afs::mbar_init(&s_bar[kBarRingFull + r], 1);
+            afs::mbar_init(&s_bar[kBarRingEmpty + r], kWarpsC);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc::fence_async_smem();
-    if (tid < 32) tc::tmem_alloc(&s_tmem, 512);
+    if (warp == 0) tc::tmem_alloc(&s_tmem, 512);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tm = s_tmem;
+    // the CTA owns the whole tensor memory (512 columns, one CTA per SM), so the allocation starts at lane 0, column 0;
+    // with a literal base every TMEM address of the issue loop is a compile-time constant
+    if (s_tmem != 0) __trap();
+    constexpr uint32_t tm = 0;
     if (tid < 128) {
         // thread = lane = row (2 k2 + part) of G; word c = {G[row][2c+1] : G[row][2c]}
 #pragma unroll
@@ -154,203 +236,331 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
                 uint32_t v[16];
 #pragma unroll
                 for (int j = 0; j < 16; j++) v[j] = __ldg(src + c0 + j);
-                tc::tmem_st16(tm + lane_base + (plane ? kColGlo : kColGhi) + c0, v);
+                tc::tmem_st16(tm + ((uint32_t)(tid & ~31) << 16) + (plane ? kColGlo : kColGhi) + c0, v);
             }
         }
         tc::tmem_wait_st();
-    }
-    // per-thread constants of the whole persistent loop
-    float win[32];
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-        win[j] = __ldg(args.hann + 64 * (32 * wg + j) + n2);
-        if (PCM16) win[j] *= (1.0f / 32768.0f);      // librosa.load's scaling, a power of two
-    }
-    // twiddles W4096^(k1 n2): wg 0 handles k1 = 32 (slot 0) and 1..15, wg 1 handles 16..31
-    float twc[16], tws[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const int k1 = wg ? 16 + i : (i == 0 ? 32 : i);
-        const float2 w = __ldg(args.tw + k1 * 64 + n2);
-        twc[i] = w.x;
-        tws[i] = w.y;
     }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
 
-    const uint32_t d_tm = tm + kColD0 + pipe * kColDStride;
-    const uint64_t a1_hi_desc = tc::smem_desc_k_sw128(s_a1_hi), a1_lo_desc = tc::smem_desc_k_sw128(s_a1_lo);
-    const uint64_t f_hi_desc = tc::smem_desc_k_sw128(s_f), f_lo_desc = tc::smem_desc_k_sw128(s_f + kFPlane);
-    const uint64_t y_hi_desc = tc::smem_desc_k_sw128(s_y_hi), y_lo_desc = tc::smem_desc_k_sw128(s_y_lo);
-    constexpr uint32_t idesc1 = tc::idesc_bf16_f32(128, kN1), idesc2 = tc::idesc_bf16_f32(128, kN2);
-    uint64_t *bar = &s_bar[pipe];
-    uint32_t phase = 0;
-    const int bar_id = 1 + pipe;
-
     const int64_t n_frames = args.frame_end - args.frame_begin;
     const int64_t n_groups = (n_frames + 3) >> 2;
-    const int64_t g_stride = 2 * (int64_t)gridDim.x;
-    int64_t g = 2 * (int64_t)blockIdx.x + pipe;
-    int track = 0;                                      // cursor of the (at most four) threads that locate frames
-    if (t < 4 && g < n_groups) s_meta[pipe][0][t] = locate_frame(args, args.frame_begin + 4 * g + t, track);
-    int par = 0;
+    const int n_local = (int)((n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x);      // groups of this CTA (>= 1: grid <= groups)
+    const int n_tiles = 2 * n_local;
+    // event trace of this warp (debugging aid, off unless the host passes a buffer): slot = 4 * index + event
+    auto trace = [&](int ev, int idx) {
+        if (TRACE && lane == 0 && 4 * idx + ev < kTraceLen)
+            args.trace[((size_t)blockIdx.x * (kThreadsA / 32) + warp) * kTraceLen + 4 * idx + ev] = clock64();
+    };
 
-    for (; g < n_groups; g += g_stride, par ^= 1) {
-        named_bar(bar_id, 256);                          // this group's frame table is visible
-        if (t < 4 && g + g_stride < n_groups)
-            s_meta[pipe][par ^ 1][t] = locate_frame(args, args.frame_begin + 4 * (g + g_stride) + t, track);
-
+    if (warp < kWarpsC) {
+        // ================= C: convert =================
+        const int ln = tid & 127, wg = tid >> 7;          // ln = TMEM lane = row (frame of the pair, n2); wg = half of n1
+        const int n2 = ln & 63, fp = ln >> 6;
+        const uint32_t lane_base = (uint32_t)(ln & ~31) << 16;
+        constexpr int kSampleBytes = PCM16 ? 2 : 4;
+        // this thread's samples of a tile: n = 64 (32 wg + r) + n2, r = 0..31; rows 0..15 come from the tile's first ring
+        // slot, rows 16..31 from the second; piece of the slot: frame fp, half wg -> piece fp + wg
+        const float *wptr = reinterpret_cast<const float *>(smem + kOffWin) + (kNfft / 2) * wg + n2;
+        const unsigned char *xptr = smem + kOffRing + (uint32_t)(fp + wg) * kPieceBytes + n2 * kSampleBytes;
+        const bool straddle_warp = fp == 1 && wg == 0;      // the half frame that is missing from the ring when the tile straddles tracks
+        const uint32_t a1_col = tm + lane_base + kColA1 + 16 * wg;
+        uint32_t stage = 0, ring_phase = 0;
 #pragma unroll 1
-        for (int pr = 0; pr < 2; pr++) {
-            const int fq = 2 * pr + fp;                  // frame of the group this row belongs to
-            // ---- convert: x[64 n1 + n2] * window -> A1[row][n1], two bf16 planes ----
-            {
-                const FrameMeta m = s_meta[pipe][par][fq];
-                const bool full = m.lo == 0 && m.hi == kNfft;
+        for (int T = 0; T < n_tiles; T++) {
+            float x[32];
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    float x[8];
+            for (int half = 0; half < 2; half++) {
+                mbar_wait_sleep(&s_bar[kBarRingFull + stage], ring_phase);
+                if (straddle_warp && !s_slot[stage].shared) {
+                    // the tile straddles two tracks (or ends the chunk): guarded loads from global memory instead
+                    const SlotInfo si = s_slot[stage];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const int n = 64 * (32 * wg + 8 * c + j) + n2;
+                    for (int r = 0; r < 16; r++) {
+                        const int n = 64 * (16 * half + r) + n2;
                         float v = 0.f;
-                        if (full || (n >= m.lo && n < m.hi)) {
-                            if (PCM16) v = (float)__ldg(static_cast<const short *>(args.audio) + m.base + n);
-                            else v = __ldg(static_cast<const float *>(args.audio) + m.base + n);
+                        if (n >= si.lo1 && n < si.hi1) {
+                            if (PCM16) v = (float)__ldg(static_cast<const short *>(args.audio) + si.base1 + n);
+                            else v = __ldg(static_cast<const float *>(args.audio) + si.base1 + n);
                         }
-                        x[j] = __fmul_rn(v, win[8 * c + j]);              // chroma.py:62 section * np.hanning
+                        x[16 * half + r] = v;
                     }
-                    uint32_t h[4], l[4];
+                } else {
+                    const unsigned char *src = xptr + stage * kSlotBytes;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) tc::split_bf16x2(x[2 * j], x[2 * j + 1], h[j], l[j]);
-                    const uint32_t off = (uint32_t)ln * 128 + ((uint32_t)((4 * wg + c) ^ (ln & 7)) << 4);
-                    sts128(s_a1_hi + off, h[0], h[1], h[2], h[3]);
-                    sts128(s_a1_lo + off, l[0], l[1], l[2], l[3]);
+                    for (int r = 0; r < 16; r++) {
+                        if (PCM16) x[16 * half + r] = (float)*reinterpret_cast<const short *>(src + 64 * r * kSampleBytes);
+                        else x[16 * half + r] = *reinterpret_cast<const float *>(src + 64 * r * kSampleBytes);
+                    }
                 }
+#pragma unroll
+                for (int r = 0; r < 16; r++) x[16 * half + r] = __fmul_rn(x[16 * half + r], wptr[64 * (16 * half + r)]);   // chroma.py:62 section * np.hanning
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_bar[kBarRingEmpty + stage]);                          // the slot's samples are in registers
+                stage = (stage + 1) & (kRingSlots - 1);
+                if (stage == 0) ring_phase ^= 1u;
             }
-            tc::fence_async_smem();
+            uint32_t h[16], l[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) tc::split_bf16x2(x[2 * j], x[2 * j + 1], h[j], l[j]);
+            pin16(h);
+            pin16(l);
+            trace(1, T);
+            // A1 is single-buffered: the MMAs of the previous tile must have read it
+            if (T > 0) mbar_wait_sleep(&s_bar[kBarM1Done + ((T - 1) & 1)], (uint32_t)(((T - 1) >> 1) & 1));
+            trace(2, T);
+            tc::tmem_st16(a1_col, h);
+            tc::tmem_st16(a1_col + 32, l);
+            tc::tmem_wait_st();
             tc::fence_before_sync();
-            named_bar(bar_id, 256);
-            if (t == 0) {
-                tc::fence_after_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_bar[kBarA1Full]);
+            trace(0, T);
+        }
+    } else if (warp < kWarpsC + kWarpsE1) {
+        // ================= E1: twiddle, split, store as rows (frame, k1) of the stage-2 B operand =================
+        const int t = tid - 32 * kWarpsC;
+        const int ln = t & 127, wg = t >> 7;
+        const int n2 = ln & 63, fp = ln >> 6;
+        const uint32_t lane_base = (uint32_t)(ln & ~31) << 16;
+        // twiddles W4096^(k1 n2): wg 0 handles k1 = 32 (slot 0) and 1..15, wg 1 handles 16..31
+        float twc[16], tws[16];
 #pragma unroll
-                for (int term = 0; term < 3; term++) {
-                    const uint64_t ad = term == 1 ? a1_lo_desc : a1_hi_desc;     // hi*hi, lo*hi, hi*lo
-                    const uint64_t bd = term == 2 ? f_lo_desc : f_hi_desc;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ks++) tc::mma_ss(d_tm, ad + 2 * ks, bd + 2 * ks, idesc1, (term | ks) != 0);
-                }
-                tc::mma_commit(bar);
-            }
-            afs::mbar_wait(bar, phase);
-            phase ^= 1u;
+        for (int i = 0; i < 16; i++) {
+            const int k1 = wg ? 16 + i : (i == 0 ? 32 : i);
+            const float2 w = __ldg(args.tw + k1 * 64 + n2);
+            twc[i] = w.x;
+            tws[i] = w.y;
+        }
+        const uint32_t kb_off = (uint32_t)(n2 >> 5) * kYBlk + (uint32_t)(n2 & 3) * 4;
+        const uint32_t cw16 = ((((uint32_t)(n2 & 31) >> 2) ^ (uint32_t)(4 * fp)) << 4);
+#pragma unroll 1
+        for (int T = 0; T < n_tiles; T++) {
+            const int s = T & 1, use = T >> 1, p = T & 1, gi = T >> 1, b = gi & 1, u = gi >> 1;
+            const uint32_t s_y_hi = s_base + kOffY + (uint32_t)b * kYBuf;
+            const int fq = 2 * p + fp;                   // frame of the group this row belongs to
+            // row = 36 fq + k1: (row & 7) = (k1 & 7) ^ 4 fp, so the swizzled 16-byte chunk is (cw16 ^ (k1 & 7) << 4) with a
+            // per-thread constant cw16; the rest of the address has bits 4..6 clear
+            const uint32_t y_row0 = s_y_hi + kb_off + (uint32_t)(fq * kRowsPerFrame) * 128;
+            auto emit = [&](int k1, float re, float im) {
+                uint32_t h, l;
+                tc::split_bf16x2(re, im, h, l);
+                const uint32_t addr = (y_row0 | (cw16 ^ (uint32_t)((k1 & 7) << 4))) + (uint32_t)k1 * 128;
+                sts32(addr, h);
+                sts32(addr + kYPlane, l);
+            };
+            mbar_wait_sleep(&s_bar[kBarM1Done + s], (uint32_t)(use & 1));
             tc::fence_after_sync();
-            // ---- epilogue 1: twiddle, split, store as rows (frame, k1) of the stage-2 B operand ----
+            trace(0, T);
+            // Y'[b] was the B operand of stage 2 two groups ago
+            if (p == 0 && u > 0) mbar_wait_sleep(&s_bar[kBarM2Done + b], (uint32_t)((u - 1) & 1));
+            const uint32_t d1 = tm + lane_base + kColD1 + 64 * s + 32 * wg;
             {
-                uint32_t v[32];
-                {
-                    uint32_t va[16], vb[16];
-                    tc::tmem_ld16(d_tm + lane_base + 32 * wg, va);
-                    tc::tmem_ld16(d_tm + lane_base + 32 * wg + 16, vb);
-                    tc::tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 16; j++) { v[j] = va[j]; v[16 + j] = vb[j]; }
-                }
-                const uint32_t kb_off = (uint32_t)(n2 >> 5) * kYBlk + (uint32_t)(n2 & 3) * 4;
-                const uint32_t cw = (uint32_t)(n2 & 31) >> 2;
-                const int row0 = fq * kRowsPerFrame;
-                auto emit = [&](int k1, float re, float im) {
-                    uint32_t h, l;
-                    tc::split_bf16x2(re, im, h, l);
-                    const uint32_t row = (uint32_t)(row0 + k1);
-                    const uint32_t off = kb_off + row * 128 + ((cw ^ (row & 7)) << 4);
-                    sts32(s_y_hi + off, h);
-                    sts32(s_y_lo + off, l);
-                };
+                uint32_t v[16];
+                tc::tmem_ld16(d1, v);
+                tc::tmem_wait_ld();
                 if (wg == 0) {
                     emit(0, __uint_as_float(v[0]), 0.f);                                   // Y[0] is real and its twiddle is 1
                     const float y32 = __uint_as_float(v[1]);                               // Y[32] is real
                     emit(32, y32 * twc[0], y32 * tws[0]);
+                }
 #pragma unroll
-                    for (int i = 1; i < 16; i++) {
-                        const float yr = __uint_as_float(v[2 * i]), yi = __uint_as_float(v[2 * i + 1]);
-                        emit(i, yr * twc[i] - yi * tws[i], yr * tws[i] + yi * twc[i]);
-                    }
-                } else {
+                for (int i = 0; i < 8; i++) {
+                    if (i == 0 && wg == 0) continue;
+                    const float yr = __uint_as_float(v[2 * i]), yi = __uint_as_float(v[2 * i + 1]);
+                    emit(16 * wg + i, yr * twc[i] - yi * tws[i], yr * tws[i] + yi * twc[i]);
+                }
+            }
+            {
+                uint32_t v[16];
+                tc::tmem_ld16(d1 + 16, v);
+                tc::tmem_wait_ld();
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_bar[kBarD1Free + s]);
+                trace(1, T);
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const float yr = __uint_as_float(v[2 * i]), yi = __uint_as_float(v[2 * i + 1]);
-                        emit(16 + i, yr * twc[i] - yi * tws[i], yr * tws[i] + yi * twc[i]);
+                for (int i = 8; i < 16; i++) {
+                    const float yr = __uint_as_float(v[2 * i - 16]), yi = __uint_as_float(v[2 * i - 15]);
+                    emit(16 * wg + i, yr * twc[i] - yi * tws[i], yr * tws[i] + yi * twc[i]);
+                }
+            }
+            tc::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_bar[kBarYFull + b]);
+            trace(2, T);
+        }
+    } else if (warp < kWarpsC + kWarpsE1 + kWarpsE2) {
+        // ================= E2: lane = (k2, re/im); |X|^2 pairs up through the neighbouring lane; wg takes two frames =================
+        const int t = tid - 32 * (kWarpsC + kWarpsE1);
+        const int ln = t & 127, wg = t >> 7;
+        const uint32_t lane_base = (uint32_t)(ln & ~31) << 16;
+        const bool odd = ln & 1;
+        for (int gi = 0; gi < n_local; gi++) {
+            const int b = gi & 1, u = gi >> 1;
+            const int64_t g = blockIdx.x + (int64_t)gi * gridDim.x;
+            mbar_wait_sleep(&s_bar[kBarM2Done + b], (uint32_t)(u & 1));
+            tc::fence_after_sync();
+            trace(0, gi);
+#pragma unroll 1
+            for (int q = 0; q < 2; q++) {
+                const int fq = 2 * wg + q;
+                uint32_t v[36];
+                {
+                    uint32_t va[16], vb[16], vc[4];
+                    const uint32_t c0 = tm + lane_base + kColD2 + fq * kRowsPerFrame;
+                    tc::tmem_ld16(c0, va);
+                    tc::tmem_ld16(c0 + 16, vb);
+                    tmem_ld4(c0 + 32, vc);
+                    tc::tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; j++) { v[j] = va[j]; v[16 + j] = vb[j]; }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[32 + j] = vc[j];
+                }
+                if (q == 1) {
+                    // everything this warp reads from D2 is in registers: the next group's stage 2 may overwrite it
+                    tc::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_bar[kBarD2Free]);
+                    trace(1, gi);
+                }
+                float own[18];
+#pragma unroll
+                for (int j = 0; j < 17; j++) {
+                    // columns k1 = 2j (kept by even lanes) and 2j + 1 (kept by odd lanes); column 33 is padding
+                    const float a = __uint_as_float(v[2 * j]), bb = __uint_as_float(v[2 * j + 1]);
+                    const float sa = a * a, sb = bb * bb;
+                    const float other = __shfl_xor_sync(0xffffffffu, odd ? sa : sb, 1);
+                    own[j] = (odd ? sb : sa) + other;
+                }
+                if (odd) own[16] = 0.f;
+                own[17] = 0.f;
+                const int64_t fl = 4 * g + fq;                           // frame inside the chunk
+                if (fl < n_frames) {
+                    uint32_t *ph = args.p_hi + fl * kPlaneWords + ln, *pl = args.p_lo + fl * kPlaneWords + ln;
+#pragma unroll
+                    for (int i = 0; i < 9; i++) {
+                        uint32_t h, l;
+                        tc::split_bf16x2(own[2 * i], own[2 * i + 1], h, l);
+                        ph[i * 128] = h;
+                        pl[i * 128] = l;
                     }
                 }
             }
+            trace(2, gi);
         }
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        named_bar(bar_id, 256);
-        if (t == 0) {
+    } else if (warp > kWarpsC + kWarpsE1 + kWarpsE2) {
+        // ================= L: audio -> ring.  A piece (1024 consecutive samples) that lies inside its track and
+        // starts 16-byte aligned is one cp.async.bulk; anything else (zero padding at the ends of a track, frames past
+        // the end of the chunk, odd track offsets) is copied by the warp with guarded loads.  Loader warp hl takes the
+        // slot of half hl of every tile; its lanes 0..2 own the three pieces =================
+        constexpr int kSampleBytes = PCM16 ? 2 : 4;
+        const int hl = warp - (kWarpsC + kWarpsE1 + kWarpsE2 + 1);
+        TrackCursor track;
+        const int pc_l = lane < 3 ? lane : 0;
+        const int n0_l = (pc_l == 0 ? 0 : 2048) + 1024 * hl;
+#pragma unroll 1
+        for (int T = 0; T < n_tiles; T++) {
+            // frames only move forward through the cursor: both frames of the tile are located once per tile
+            const int64_t g = blockIdx.x + (int64_t)(T >> 1) * gridDim.x;
+            const int64_t f0 = args.frame_begin + 4 * g + 2 * (T & 1);
+            const FrameMeta m0 = locate_frame(args, f0, track);
+            const FrameMeta m1 = locate_frame(args, f0 + 1, track);
+            // frame 1's first half is the same run of real samples as frame 0's second half
+            const bool shared = m1.hi > 0 && m1.lo == 0 && m0.hi == kNfft && m1.base == m0.base + kNfft / 2;
+            const long long base_l = pc_l == 2 ? m1.base : m0.base;
+            const int lo_l = pc_l == 2 ? m1.lo : m0.lo, hi_l = pc_l == 2 ? m1.hi : m0.hi;
+            const char *src_l = static_cast<const char *>(args.audio) + (base_l + n0_l) * kSampleBytes;
+            const bool bulk_l = lane < 3 && n0_l >= lo_l && n0_l + 1024 <= hi_l && (reinterpret_cast<uintptr_t>(src_l) & 15) == 0;
+            const unsigned qmask = __ballot_sync(0xffffffffu, bulk_l) & 7u;
+            const int k = 2 * T + hl, stage = k % kRingSlots, ruse = k / kRingSlots;
+            if (ruse > 0) mbar_wait_sleep(&s_bar[kBarRingEmpty + stage], (uint32_t)((ruse - 1) & 1));
+            unsigned char *slot = smem + kOffRing + stage * kSlotBytes;
+            if (qmask != 7u) {
+                // guarded pieces first, so that the one arrival below (release) also publishes them
+#pragma unroll
+                for (int pc = 0; pc < 3; pc++) {
+                    if (qmask & (1u << pc)) continue;
+                    const FrameMeta &fm = pc == 2 ? m1 : m0;
+                    const int n0 = (pc == 0 ? 0 : 2048) + 1024 * hl;
+                    unsigned char *dst = slot + pc * kPieceBytes;
+                    for (int i = lane; i < 1024; i += 32) {
+                        const int n = n0 + i;
+                        const bool in = n >= fm.lo && n < fm.hi;
+                        if (PCM16) reinterpret_cast<short *>(dst)[i] = in ? __ldg(static_cast<const short *>(args.audio) + fm.base + n) : (short)0;
+                        else reinterpret_cast<float *>(dst)[i] = in ? __ldg(static_cast<const float *>(args.audio) + fm.base + n) : 0.f;
+                    }
+                }
+            }
+            if (lane == 0) {
+                SlotInfo si;
+                si.base1 = m1.base; si.lo1 = m1.lo; si.hi1 = m1.hi; si.shared = shared ? 1 : 0; si.pad = 0;
+                s_slot[stage] = si;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (qmask) afs::mbar_expect_tx(&s_bar[kBarRingFull + stage], (uint32_t)__popc(qmask) * 1024 * kSampleBytes);
+                else mbar_arrive(&s_bar[kBarRingFull + stage]);
+            }
+            __syncwarp();
+            if (bulk_l) afs::bulk_g2s(slot + pc_l * kPieceBytes, src_l, 1024 * kSampleBytes, &s_bar[kBarRingFull + stage]);
+            trace(0, T);
+        }
+    } else {
+        // ================= M: the warp that issues tensor-core work (converged; one elected lane issues) =================
+        const uint64_t f_hi_desc = tc::smem_desc_k_sw128(s_base + kOffF), f_lo_desc = tc::smem_desc_k_sw128(s_base + kOffF + kFPlane);
+        constexpr uint32_t idesc1 = tc::idesc_bf16_f32(128, kN1), idesc2 = tc::idesc_bf16_f32(128, kN2);
+        auto stage1 = [&](int T) {
+            const int s = T & 1, use = T >> 1;
+            mbar_wait_sleep(&s_bar[kBarA1Full], (uint32_t)(T & 1));
+            if (use > 0) mbar_wait_sleep(&s_bar[kBarD1Free + s], (uint32_t)((use - 1) & 1));
             tc::fence_after_sync();
+            trace(0, T);
+            const uint32_t d1 = tm + kColD1 + 64 * s, a_hi = tm + kColA1, a_lo = a_hi + 32;
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) tc::mma_ts_elect(d1, a_hi + 8 * ks, f_hi_desc + 2 * ks, idesc1, ks != 0);     // x_hi F_hi
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) tc::mma_ts_elect(d1, a_lo + 8 * ks, f_hi_desc + 2 * ks, idesc1, 1u);          // x_lo F_hi
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) tc::mma_ts_elect(d1, a_hi + 8 * ks, f_lo_desc + 2 * ks, idesc1, 1u);          // x_hi F_lo
+            tc::mma_commit_elect(&s_bar[kBarM1Done + s]);
+            trace(1, T);
+        };
+        auto stage2 = [&](int gi) {
+            const int b = gi & 1, u = gi >> 1;
+            mbar_wait_sleep(&s_bar[kBarYFull + b], (uint32_t)(u & 1));
+            if (gi > 0) mbar_wait_sleep(&s_bar[kBarD2Free], (uint32_t)((gi - 1) & 1));
+            tc::fence_after_sync();
+            trace(2, gi);
+            const uint64_t y_hi_desc = tc::smem_desc_k_sw128(s_base + kOffY + (uint32_t)b * kYBuf);
+            const uint64_t y_lo_desc = tc::smem_desc_k_sw128(s_base + kOffY + (uint32_t)b * kYBuf + kYPlane);
 #pragma unroll
             for (int term = 0; term < 3; term++) {
                 const uint32_t a_tm = tm + (term == 1 ? kColGlo : kColGhi);           // hi*hi, lo*hi, hi*lo
                 const uint64_t bd = term == 2 ? y_lo_desc : y_hi_desc;
 #pragma unroll
                 for (int ks = 0; ks < 8; ks++)
-                    tc::mma_ts(d_tm, a_tm + 8 * ks, bd + (uint64_t)(((ks >> 2) * kYBlk + (ks & 3) * 32) >> 4), idesc2, (term | ks) != 0);
+                    tc::mma_ts_elect(tm + kColD2, a_tm + 8 * ks, bd + (uint64_t)(((ks >> 2) * kYBlk + (ks & 3) * 32) >> 4), idesc2, (term | ks) != 0);
             }
-            tc::mma_commit(bar);
+            tc::mma_commit_elect(&s_bar[kBarM2Done + b]);
+            trace(3, gi);
+        };
+        // issue order: the single-buffered A1 is refilled while the previous group's stage 2 keeps the tensor pipe busy
+        for (int gi = 0; gi < n_local; gi++) {
+            stage1(2 * gi);
+            if (gi > 0) stage2(gi - 1);
+            stage1(2 * gi + 1);
         }
-        afs::mbar_wait(bar, phase);
-        phase ^= 1u;
-        tc::fence_after_sync();
-        // ---- epilogue 2: lane = (k2, re/im); |X|^2 pairs up through the neighbouring lane; wg takes two frames ----
-#pragma unroll 1
-        for (int q = 0; q < 2; q++) {
-            const int fq = 2 * wg + q;
-            uint32_t v[36];
-            {
-                uint32_t va[16], vb[16], vc[4];
-                const uint32_t c0 = d_tm + lane_base + fq * kRowsPerFrame;
-                tc::tmem_ld16(c0, va);
-                tc::tmem_ld16(c0 + 16, vb);
-                tmem_ld4(c0 + 32, vc);
-                tc::tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 16; j++) { v[j] = va[j]; v[16 + j] = vb[j]; }
-#pragma unroll
-                for (int j = 0; j < 4; j++) v[32 + j] = vc[j];
-            }
-            const bool odd = ln & 1;
-            float own[18];
-#pragma unroll
-            for (int j = 0; j < 17; j++) {
-                // columns k1 = 2j (kept by even lanes) and 2j + 1 (kept by odd lanes); column 33 is padding
-                const float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
-                const float sa = a * a, sb = b * b;
-                const float other = __shfl_xor_sync(0xffffffffu, odd ? sa : sb, 1);
-                own[j] = (odd ? sb : sa) + other;
-            }
-            if (odd) own[16] = 0.f;
-            own[17] = 0.f;
-            const FrameMeta m = s_meta[pipe][par][fq];
-            if (m.valid) {
-                const int64_t fl = 4 * g + fq;                       // frame inside the chunk
-                uint32_t *ph = args.p_hi + fl * kPlaneWords + ln, *pl = args.p_lo + fl * kPlaneWords + ln;
-#pragma unroll
-                for (int i = 0; i < 9; i++) {
-                    uint32_t h, l;
-                    tc::split_bf16x2(own[2 * i], own[2 * i + 1], h, l);
-                    ph[i * 128] = h;
-                    pl[i * 128] = l;
-                }
-            }
-        }
-        tc::fence_before_sync();      // the next group's MMAs overwrite the accumulator columns read above
+        stage2(n_local - 1);
+        // drain: the last commit covers every MMA issued before it
+        mbar_wait_sleep(&s_bar[kBarM2Done + ((n_local - 1) & 1)], (uint32_t)(((n_local - 1) >> 1) & 1));
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (tid < 32) tc::tmem_dealloc(tm, 512);
+    if (warp == 0) tc::tmem_dealloc(tm, 512);
 }
 
 // ---------------- kernel B: filterbank + normalisation ----------------
@@ -582,7 +792,7 @@ int chroma_tc_create(afs_chroma_tc **out, const std::vector<double> &fb, const s
             f_img[off] = hi;
             f_img[kFPlane / 2 + off] = lo;
         }
-    // ---- G as the TMEM A operand: row 2 k2 + part, K = 2 n2 + (re | im of Y') ----
+    // ---- G as the TMEM A operand: row 2 k2 + part, K = 2 n2 + (re | im of Y'); lane = row, word c = K elements 2c, 2c + 1 ----
     std::vector<uint32_t> g_img((size_t)2 * 128 * 64);
     for (int k2 = 0; k2 < 64; k2++)
         for (int n2 = 0; n2 < 64; n2++) {
@@ -641,8 +851,10 @@ int chroma_tc_create(afs_chroma_tc **out, const std::vector<double> &fb, const s
         chroma_tc_destroy(tcp);
         return rc;
     }
-    cudaError_t e = cudaFuncSetAttribute(chroma_tc_spectrum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemA);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(chroma_tc_spectrum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemA);
+    cudaError_t e = cudaFuncSetAttribute(chroma_tc_spectrum_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemA);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chroma_tc_spectrum_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemA);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chroma_tc_spectrum_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemA);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chroma_tc_spectrum_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemA);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chroma_tc_filterbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFb);
     if (e != cudaSuccess) {
         chroma_tc_destroy(tcp);
@@ -686,13 +898,36 @@ int chroma_tc_run(afs_chroma_tc *tcp, const ChromaBatch &bt, cudaStream_t st)
         sa.hann = tcp->hann;
         sa.p_hi = tcp->scratch;
         sa.p_lo = tcp->scratch + (size_t)tcp->scratch_frames * kPlaneWords;
+        sa.trace = nullptr;
+        // AFS_CHROMA_TC_TRACE=<file>: clock64 stamps of every warp's pipeline events in the first chunk (debugging aid)
+        const char *trace_path = f0 == 0 ? getenv("AFS_CHROMA_TC_TRACE") : nullptr;
+        const size_t trace_n = (size_t)n_sm * (kThreadsA / 32) * kTraceLen;
+        if (trace_path) {
+            AFS_CUDA(cudaMalloc(&sa.trace, trace_n * sizeof(long long)));
+            AFS_CUDA(cudaMemsetAsync(sa.trace, 0, trace_n * sizeof(long long), st));
+        }
         const int64_t groups = (f1 - f0 + 3) / 4;
-        int64_t blocks = (groups + 1) / 2;
+        int64_t blocks = groups;
         if (blocks > n_sm) blocks = n_sm;
-        if (bt.pcm16) chroma_tc_spectrum_kernel<true><<<(unsigned)blocks, kThreadsA, kSmemA, st>>>(sa);
-        else chroma_tc_spectrum_kernel<false><<<(unsigned)blocks, kThreadsA, kSmemA, st>>>(sa);
+        if (sa.trace) {
+            if (bt.pcm16) chroma_tc_spectrum_kernel<true, true><<<(unsigned)blocks, kThreadsA, kSmemA, st>>>(sa);
+            else chroma_tc_spectrum_kernel<false, true><<<(unsigned)blocks, kThreadsA, kSmemA, st>>>(sa);
+        } else if (bt.pcm16) chroma_tc_spectrum_kernel<true, false><<<(unsigned)blocks, kThreadsA, kSmemA, st>>>(sa);
+        else chroma_tc_spectrum_kernel<false, false><<<(unsigned)blocks, kThreadsA, kSmemA, st>>>(sa);
         afs::count_launch();
         AFS_CUDA(cudaGetLastError());
+        if (trace_path) {
+            std::vector<long long> host(trace_n);
+            AFS_CUDA(cudaMemcpyAsync(host.data(), sa.trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost, st));
+            AFS_CUDA(cudaStreamSynchronize(st));
+            cudaFree(sa.trace);
+            if (FILE *fp = fopen(trace_path, "wb")) {
+                const int hdr[4] = {n_sm, kThreadsA / 32, kTraceLen, (int)blocks};
+                fwrite(hdr, sizeof(int), 4, fp);
+                fwrite(host.data(), sizeof(long long), trace_n, fp);
+                fclose(fp);
+            }
+        }
         FilterbankArgs fa;
         fa.p_hi = sa.p_hi;
         fa.p_lo = sa.p_lo;
