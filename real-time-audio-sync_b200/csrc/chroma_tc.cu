@@ -47,11 +47,13 @@ constexpr int kChroma = 12;
 //   warp  24      M   one thread issues every tcgen05.mma; completion is tracked with tcgen05.commit -> mbarrier
 //   warps 25, 26  L   loaders: TMA bulk copies (cp.async.bulk) of the audio into a shared-memory ring; issuing a copy or an
 //                     mbarrier transaction costs a warp 100-200 cycles, so two warps take alternate slots
+//   warp  27      P   publisher: the gpu-scope release of a stored group (and the check that its ring slot is free) take
+//                     a round trip to L2, so they run here and not in the epilogue warps
 // The roles only meet through mbarriers, so while the tensor pipe works on one tile the converters are two tiles
 // ahead and the two epilogues drain the previous results.
 constexpr int kWarpsC = 8, kWarpsE1 = 8, kWarpsE2 = 8;
 constexpr int kWarpsL = 2;
-constexpr int kThreadsA = 32 * (kWarpsC + kWarpsE1 + kWarpsE2 + 1 + kWarpsL);      // 864: + M + L
+constexpr int kThreadsA = 32 * (kWarpsC + kWarpsE1 + kWarpsE2 + 1 + kWarpsL + 1);      // 896: + M + L + P
 constexpr int kRowsPerFrame = 36;              // 33 k1 rows + 3 pad rows (N of stage 2 must be a multiple of 16)
 constexpr int kN1 = 64;                        // stage-1 N: 64 real outputs
 constexpr int kN2 = 4 * kRowsPerFrame;         // stage-2 N: 144
@@ -74,8 +76,8 @@ constexpr uint32_t kSmemA = kOffRing + kRingSlots * kSlotBytes;          // 229 
 // TMEM columns: G_hi [0,64) | G_lo [64,128) | A1 hi [128,160) lo [160,192) | D1[s] [192 + 64 s, +64) | D2 [320, 464)
 constexpr uint32_t kColGhi = 0, kColGlo = 64, kColA1 = 128, kColD1 = 192, kColD2 = 320;
 // mbarriers
-enum { kBarA1Full = 0, kBarM1Done = 1, kBarD1Free = 3, kBarYFull = 5, kBarM2Done = 7, kBarD2Free = 9, kBarRingFull = 10,
-       kBarRingEmpty = 10 + kRingSlots, kNumBars = 10 + 2 * kRingSlots };
+enum { kBarA1Full = 0, kBarM1Done = 1, kBarD1Free = 3, kBarYFull = 5, kBarM2Done = 7, kBarD2Free = 9, kBarStored = 10, kBarSlotOk = 11,
+       kBarRingFull = 12, kBarRingEmpty = 12 + kRingSlots, kNumBars = 12 + 2 * kRingSlots };
 
 // what the loader tells the converters about a ring slot
 struct SlotInfo {
@@ -100,7 +102,16 @@ struct SpectrumArgs {
     const uint32_t *g_img;                     // [2][128][64] words: TMEM images of G hi | lo
     const float2 *tw;                          // [33][64]: W4096^(k1 n2) = (cos, -sin)
     const float *hann;                         // 4096
-    uint32_t *p_hi, *p_lo;                     // [frame - frame_begin][kPlaneWords]
+    // power spectrum ring (global memory, sized to stay in L2): tile slot = 64 frames, planes hi | lo
+    uint32_t *p_hi, *p_lo;                     // [ring_tiles * 64][kPlaneWords]
+    int ring_tiles;
+    int *prod, *cons;                          // per slot: groups stored so far / times consumed so far (monotonic)
+    int n_fb, n_spec;                          // CTAs [0, n_fb) run the filterbank role, the rest the spectrum role
+    // filterbank role
+    const uint4 *w_img;                        // [36][4 KB]
+    const int64_t *out_off;
+    int normalize, out_f64;
+    void *out;
     long long *trace;                          // optional (AFS_CHROMA_TC_TRACE): [block][warp][kTraceLen] clock64 stamps
 };
 constexpr int kTraceLen = 256;
@@ -113,18 +124,6 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
                  : "memory");
 }
 
-__device__ __forceinline__ float ldg_stream(const float *p)
-{
-    float v;
-    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float ldg_stream(const short *p)
-{
-    short v;
-    asm volatile("ld.global.L1::no_allocate.s16 %0, [%1];" : "=h"(v) : "l"(p));
-    return (float)v;
-}
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 // mbarrier wait with a long suspend-time hint: the warp sleeps in hardware until the phase completes instead of
 // re-issuing try_wait every few hundred cycles (a third of all issued instructions in the first profile were such spins)
@@ -134,7 +133,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
     do {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done)
-                     : "r"(afs::smem_addr(bar)), "r"(parity), "r"(1000000u)
+                     : "r"(afs::smem_addr(bar)), "r"(parity), "r"(20000u)
                      : "memory");
     } while (!done);
 }
@@ -177,6 +176,221 @@ __device__ __forceinline__ FrameMeta locate_frame(const SpectrumArgs &a, int64_t
     return m;
 }
 
+// ---------------- filterbank role: [64 frames x (hi | lo) planes] x [bins x 12] + normalisation ----------------
+// Runs on a few CTAs of the same launch: it consumes tiles of 64 frames from the power-spectrum ring as soon as the 16
+// spectrum CTAs that produce a tile have stored their groups (prod counter, release/acquire through L2) and hands the
+// slot back (cons counter).  The ring is a few tens of MB, so the power spectrum never leaves L2.  A tile slot is laid
+// out as the shared-memory image of the MMA's A operand — [36 K blocks][128 rows][128 B, 128-byte swizzle], row
+// 2 r + plane for frame r — so one cp.async.bulk of 16 KB per K block brings it in.
+//   warp 0      producer: waits for the tile, streams its 36 K blocks through a 3-stage ring, two K blocks (32 KB) per bulk
+//               copy — an mbarrier transaction or a bulk copy costs the issuing warp 100-200 cycles, so few and large ones
+//   warp 1      MMA issuer (elected lane): 8 MMAs (N = 32) per stage into one of two TMEM accumulators, which start from
+//               zero (cleared by the epilogue).  (Two issuer warps on alternate K blocks were tried: the kernel hangs.)
+//   warps 2..5  epilogue: TMEM -> add the hi/lo partial products (neighbouring lanes) -> normalise -> store
+constexpr int kFbTile = 64;                      // frames per tile
+constexpr int kFbGroups = kFbTile / 4;           // spectrum groups per tile
+constexpr int kFbKBlocks = kPlaneWords * 2 / 64; // 36 blocks of 64 bf16
+constexpr int kFbStages = 3;                     // of kFbStageBlocks K blocks each
+constexpr int kFbStageBlocks = 2;
+#ifndef AFS_FB_MMA_WARPS
+#define AFS_FB_MMA_WARPS 1
+#endif
+constexpr int kFbMmaWarps = AFS_FB_MMA_WARPS;
+constexpr int kFbWarps = 5 + kFbMmaWarps;
+// weights per K block: 24 rows (12 hi | 12 lo) x 64 elements.  The MMA reads N = 32 rows: rows 24..31 alias the first
+// eight rows of the next K block (behind the last block: the first A stage) and only fill accumulator columns 24..31,
+// which nobody reads.
+constexpr uint32_t kFbWBlk = 24 * 128;
+constexpr uint32_t kFbABlk = 128 * 128;
+constexpr uint32_t kFbTileBytes = kFbKBlocks * kFbABlk;                      // 589 824 B per ring slot
+constexpr uint32_t kFbStageBytes = kFbStageBlocks * kFbABlk;
+constexpr uint32_t kSmemFb = kFbKBlocks * kFbWBlk + kFbStages * kFbStageBytes;     // 110 592 + 98 304
+static_assert(kSmemFb <= kSmemA, "the filterbank role lives in the spectrum kernel's shared memory");
+enum { kFbBarFull = 0, kFbBarFree = kFbStages, kFbBarAccFull = 2 * kFbStages, kFbBarAccFree = 2 * kFbStages + 2, kFbNumBars = 2 * kFbStages + 4 };
+
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+template <bool TRACE>
+__device__ __noinline__ void filterbank_role(const SpectrumArgs &args, unsigned char *smem)
+{
+    __shared__ uint32_t s_tmem_fb;
+    __shared__ __align__(8) uint64_t s_fbar[kFbNumBars];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp >= kFbWarps) return;
+    constexpr int kThreads = 32 * kFbWarps;
+    const uint32_t s_w = afs::smem_addr(smem), s_a = s_w + kFbKBlocks * kFbWBlk;
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (int i = tid; i < (int)(kFbKBlocks * kFbWBlk / 16); i += kThreads) dst[i] = __ldg(args.w_img + i);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kFbStages; s++) {
+            afs::mbar_init(&s_fbar[kFbBarFull + s], 1);
+            afs::mbar_init(&s_fbar[kFbBarFree + s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            afs::mbar_init(&s_fbar[kFbBarAccFull + a], kFbMmaWarps);
+            afs::mbar_init(&s_fbar[kFbBarAccFree + a], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc::fence_async_smem();
+    if (warp == 0) tc::tmem_alloc(&s_tmem_fb, 64);
+    tc::fence_before_sync();
+    named_bar(1, kThreads);
+    tc::fence_after_sync();
+    const uint32_t tm = s_tmem_fb;
+    if (warp >= 1 + kFbMmaWarps) {
+        // both accumulators start from zero
+        uint32_t z[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) z[j] = 0u;
+#pragma unroll
+        for (int c = 0; c < 64; c += 16) tc::tmem_st16(tm + ((uint32_t)((warp & 3) * 32) << 16) + c, z);
+        tc::tmem_wait_st();
+    }
+    tc::fence_before_sync();
+    named_bar(1, kThreads);
+    tc::fence_after_sync();
+
+    const int64_t n_frames = args.frame_end - args.frame_begin;
+    const int64_t n_groups = (n_frames + 3) >> 2;
+    const int64_t n_tiles = (n_frames + kFbTile - 1) / kFbTile;
+    const unsigned char *ring = reinterpret_cast<const unsigned char *>(args.p_hi);
+    auto trace = [&](int ev, int idx) {
+        if (TRACE && lane == 0 && 4 * idx + ev < 256)
+            args.trace[((size_t)(args.n_spec + blockIdx.x) * (kThreadsA / 32) + warp) * 256 + 4 * idx + ev] = clock64();
+    };
+
+    if (warp == 0) {
+        // ================= producer =================
+        uint32_t seq = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += args.n_fb) {
+            const int slot = (int)(tile % args.ring_tiles), use = (int)(tile / args.ring_tiles);
+            if (lane == 0) {
+                const int64_t left = n_groups - tile * kFbGroups;
+                const int want = use * kFbGroups + (int)(left < kFbGroups ? left : kFbGroups);
+                while (afs::ld_acquire(args.prod + slot) < want) __nanosleep(100);
+                // the tile was written with ordinary stores by other SMs; the bulk copies below read it through the async proxy
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+            }
+            __syncwarp();
+            const unsigned char *src = ring + (size_t)slot * kFbTileBytes;
+            for (int kb = 0; kb < kFbKBlocks; kb += kFbStageBlocks, seq++) {
+                const uint32_t st = seq % kFbStages, u = seq / kFbStages;
+                if (u > 0) afs::mbar_wait(&s_fbar[kFbBarFree + st], (u - 1) & 1);
+                trace(0, seq);
+                if (lane == 0) {
+                    afs::mbar_expect_tx(&s_fbar[kFbBarFull + st], kFbStageBytes);
+                    afs::bulk_g2s(smem + kFbKBlocks * kFbWBlk + st * kFbStageBytes, src + (size_t)kb * kFbABlk, kFbStageBytes, &s_fbar[kFbBarFull + st]);
+                }
+                __syncwarp();
+                trace(1, seq);
+            }
+        }
+    } else if (warp <= kFbMmaWarps) {
+        // ================= MMA issuers: warp 1 takes the even K blocks, warp 2 the odd ones =================
+        constexpr uint32_t idesc = tc::idesc_bf16_f32(128, 32);
+        const uint64_t w_desc = tc::smem_desc_k_sw128(s_w), a_desc = tc::smem_desc_k_sw128(s_a);
+        const int mw = warp - 1;
+        uint32_t seq = 0, it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += args.n_fb, it++) {
+            const uint32_t acc = it & 1, au = it >> 1;
+            if (au > 0) afs::mbar_wait(&s_fbar[kFbBarAccFree + acc], (au - 1) & 1);
+            tc::fence_after_sync();
+            for (int kb = 0; kb < kFbKBlocks; kb += kFbStageBlocks, seq++) {
+                if ((int)(seq % kFbMmaWarps) != mw) continue;
+                const uint32_t st = seq % kFbStages, u = seq / kFbStages;
+                trace(2, seq);
+                afs::mbar_wait(&s_fbar[kFbBarFull + st], u & 1);
+                tc::fence_after_sync();
+                trace(0, seq);
+#pragma unroll
+                for (int b2 = 0; b2 < kFbStageBlocks; b2++) {
+                    const uint64_t ad = a_desc + (uint64_t)((st * kFbStageBytes + b2 * kFbABlk) >> 4);
+                    const uint64_t wd = w_desc + (uint64_t)(((uint32_t)(kb + b2) * kFbWBlk) >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) tc::mma_ss_elect(tm + 32 * acc, ad + 2 * ks, wd + 2 * ks, idesc, 1u);
+                }
+                tc::mma_commit_elect(&s_fbar[kFbBarFree + st]);
+                trace(1, seq);
+            }
+            tc::mma_commit_elect(&s_fbar[kFbBarAccFull + acc]);
+        }
+    } else {
+        // ================= epilogue: warp w reads TMEM lanes 32 (w % 4) ..; lane 2 r + plane belongs to frame r =================
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const int r = ((warp & 3) * 32 + lane) >> 1;             // frame of the tile
+        const bool lo_plane = lane & 1;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += args.n_fb, it++) {
+            const uint32_t acc = it & 1, au = it >> 1;
+            // this lane's output frame, located while the tile is being accumulated
+            const int64_t f = args.frame_begin + tile * kFbTile + r;
+            const bool okf = !lo_plane && f < args.frame_end;
+            int trk = 0;
+            if (okf) {
+                int lo = 0, hi = args.n_tracks;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (__ldg(args.frame_off + mid) <= f) lo = mid; else hi = mid;
+                }
+                trk = lo;
+            }
+            afs::mbar_wait(&s_fbar[kFbBarAccFull + acc], au & 1);
+            tc::fence_after_sync();
+            // all MMAs of the tile are done, so every K block has left the ring slot: hand it back to the spectrum CTAs
+            if (warp == 1 + kFbMmaWarps && lane == 0)
+                afs::st_release(args.cons + (int)(tile % args.ring_tiles), (int)(tile / args.ring_tiles) + 1);
+            uint32_t va[16], vb[16];
+            tc::tmem_ld16(tm + lane_base + 32 * acc, va);
+            tc::tmem_ld16(tm + lane_base + 32 * acc + 16, vb);
+            tc::tmem_wait_ld();
+            {
+                uint32_t z[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) z[j] = 0u;
+                tc::tmem_st16(tm + lane_base + 32 * acc, z);
+                tc::tmem_st16(tm + lane_base + 32 * acc + 16, z);
+                tc::tmem_wait_st();
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_fbar[kFbBarAccFree + acc]);
+            float raw[kChroma];
+            float ss = 0.f;
+#pragma unroll
+            for (int c = 0; c < kChroma; c++) {
+                // columns c: w_hi, 12 + c: w_lo; the lo-plane lane only contributes its w_hi product (lo * lo is noise)
+                const float w_lo_part = __uint_as_float(12 + c < 16 ? va[(12 + c) & 15] : vb[(12 + c) & 15]);
+                const float mine = lo_plane ? __uint_as_float(va[c]) : __uint_as_float(va[c]) + w_lo_part;
+                raw[c] = mine + __shfl_down_sync(0xffffffffu, mine, 1);                 // chroma.py:70 np.dot(chromafb, spec)
+                ss = fmaf(raw[c], raw[c], ss);
+            }
+            if (okf) {
+                float len = 1.f;
+                if (args.normalize) {
+                    // librosa.util.normalize(norm=2, axis=0), chroma.py:74: tiny lengths -> 1
+                    len = sqrtf(ss);
+                    if (len < FLT_MIN) len = 1.f;
+                }
+                const int64_t m = f - __ldg(args.frame_off + trk);
+                const int64_t fk = __ldg(args.frame_off + trk + 1) - __ldg(args.frame_off + trk);
+                const int64_t ob = kChroma * __ldg(args.out_off + trk) + m;
+#pragma unroll
+                for (int c = 0; c < kChroma; c++) {
+                    const float val = args.normalize ? raw[c] / len : raw[c];
+                    if (args.out_f64) static_cast<double *>(args.out)[ob + (int64_t)c * fk] = (double)val;
+                    else static_cast<float *>(args.out)[ob + (int64_t)c * fk] = val;
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    named_bar(1, kThreads);
+    if (warp == 0) tc::tmem_dealloc(tm, 64);
+}
+
 template <bool PCM16, bool TRACE>
 __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const SpectrumArgs args)
 {
@@ -185,8 +399,13 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
     __shared__ __align__(8) uint64_t s_bar[kNumBars];
     __shared__ __align__(16) SlotInfo s_slot[kRingSlots];
 
+    if ((int)blockIdx.x < args.n_fb) {
+        filterbank_role<TRACE>(args, smem);
+        return;
+    }
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t s_base = afs::smem_addr(smem);
+    const int sb = (int)blockIdx.x - args.n_fb;      // index among the spectrum CTAs
 
     // ---- one-time setup: operand images, zeroed Y' tiles (pad rows stay zero), window, barriers, TMEM, G_hi -> TMEM ----
     {
@@ -211,6 +430,8 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
             afs::mbar_init(&s_bar[kBarM2Done + s], 1);
         }
         afs::mbar_init(&s_bar[kBarD2Free], kWarpsE2);
+        afs::mbar_init(&s_bar[kBarStored], kWarpsE2);
+        afs::mbar_init(&s_bar[kBarSlotOk], 1);
         for (int r = 0; r < kRingSlots; r++) {
             afs::mbar_init(&s_bar[kBarRingFull + r], 1);
             afs::mbar_init(&s_bar[kBarRingEmpty + r], kWarpsC);
@@ -247,12 +468,12 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
 
     const int64_t n_frames = args.frame_end - args.frame_begin;
     const int64_t n_groups = (n_frames + 3) >> 2;
-    const int n_local = (int)((n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x);      // groups of this CTA (>= 1: grid <= groups)
+    const int n_local = (int)((n_groups - sb + args.n_spec - 1) / args.n_spec);      // groups of this CTA (>= 1: grid <= groups)
     const int n_tiles = 2 * n_local;
     // event trace of this warp (debugging aid, off unless the host passes a buffer): slot = 4 * index + event
     auto trace = [&](int ev, int idx) {
         if (TRACE && lane == 0 && 4 * idx + ev < kTraceLen)
-            args.trace[((size_t)blockIdx.x * (kThreadsA / 32) + warp) * kTraceLen + 4 * idx + ev] = clock64();
+            args.trace[((size_t)sb * (kThreadsA / 32) + warp) * kTraceLen + 4 * idx + ev] = clock64();
     };
 
     if (warp < kWarpsC) {
@@ -400,7 +621,9 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
         const bool odd = ln & 1;
         for (int gi = 0; gi < n_local; gi++) {
             const int b = gi & 1, u = gi >> 1;
-            const int64_t g = blockIdx.x + (int64_t)gi * gridDim.x;
+            const int64_t g = sb + (int64_t)gi * args.n_spec;
+            const int64_t ring_tile = g / kFbGroups;
+            const int ring_slot = (int)(ring_tile % args.ring_tiles), ring_use = (int)(ring_tile / args.ring_tiles);
             mbar_wait_sleep(&s_bar[kBarM2Done + b], (uint32_t)(u & 1));
             tc::fence_after_sync();
             trace(0, gi);
@@ -438,18 +661,62 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
                 }
                 if (odd) own[16] = 0.f;
                 own[17] = 0.f;
-                const int64_t fl = 4 * g + fq;                           // frame inside the chunk
+                const int64_t fl = 4 * g + fq;                           // frame of the launch
+                if (q == 0) mbar_wait_sleep(&s_bar[kBarSlotOk], (uint32_t)(gi & 1));     // the ring slot is free (publisher warp)
                 if (fl < n_frames) {
-                    uint32_t *ph = args.p_hi + fl * kPlaneWords + ln, *pl = args.p_lo + fl * kPlaneWords + ln;
+                    // A-operand image of the filterbank tile: word i * 128 + ln of the frame's plane -> K block 4 i + ln / 32,
+                    // row 2 r + plane, 16-byte chunk ((ln % 32) / 4) ^ (row & 7)
+                    const uint32_t r = (uint32_t)(fl & (kFbTile - 1));
+                    unsigned char *base = reinterpret_cast<unsigned char *>(args.p_hi) + (size_t)ring_slot * kFbTileBytes +
+                                          (uint32_t)(ln >> 5) * kFbABlk + (uint32_t)(ln & 3) * 4;
+                    const uint32_t row_hi = 2 * r, row_lo = 2 * r + 1, ch = (uint32_t)(ln & 31) >> 2;
+                    uint32_t *ph = reinterpret_cast<uint32_t *>(base + row_hi * 128 + ((ch ^ (row_hi & 7)) << 4));
+                    uint32_t *pl = reinterpret_cast<uint32_t *>(base + row_lo * 128 + ((ch ^ (row_lo & 7)) << 4));
 #pragma unroll
                     for (int i = 0; i < 9; i++) {
                         uint32_t h, l;
                         tc::split_bf16x2(own[2 * i], own[2 * i + 1], h, l);
-                        ph[i * 128] = h;
-                        pl[i * 128] = l;
+                        ph[i * (4 * kFbABlk / 4)] = h;
+                        pl[i * (4 * kFbABlk / 4)] = l;
                     }
                 }
             }
+            // the group is stored: the publisher warp releases it at gpu scope
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_bar[kBarStored]);
+            trace(2, gi);
+        }
+    } else if (warp == kWarpsC + kWarpsE1 + kWarpsE2 + 1 + kWarpsL) {
+        // ================= P: ring-slot hand-shake with the filterbank CTAs =================
+        auto slot_of = [&](int gi, int &slot, int &use) {
+            const int64_t tile = (sb + (int64_t)gi * args.n_spec) / kFbGroups;
+            slot = (int)(tile % args.ring_tiles);
+            use = (int)(tile / args.ring_tiles);
+        };
+        auto wait_slot_free = [&](int gi) {
+            int slot, use;
+            slot_of(gi, slot, use);
+            if (lane == 0) {
+                // the slot's previous tile must have been consumed by its filterbank CTA
+                while (afs::ld_acquire(args.cons + slot) < use) __nanosleep(100);
+                mbar_arrive(&s_bar[kBarSlotOk]);
+            }
+            __syncwarp();
+        };
+        wait_slot_free(0);
+        for (int gi = 0; gi < n_local; gi++) {
+            int slot, use;
+            slot_of(gi, slot, use);
+            mbar_wait_sleep(&s_bar[kBarStored], (uint32_t)(gi & 1));
+            trace(0, gi);
+            if (lane == 0) {
+                __threadfence();
+                trace(3, gi);
+                atomicAdd(args.prod + slot, 1);
+            }
+            __syncwarp();
+            trace(1, gi);
+            if (gi + 1 < n_local) wait_slot_free(gi + 1);
             trace(2, gi);
         }
     } else if (warp > kWarpsC + kWarpsE1 + kWarpsE2) {
@@ -465,7 +732,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
 #pragma unroll 1
         for (int T = 0; T < n_tiles; T++) {
             // frames only move forward through the cursor: both frames of the tile are located once per tile
-            const int64_t g = blockIdx.x + (int64_t)(T >> 1) * gridDim.x;
+            const int64_t g = sb + (int64_t)(T >> 1) * args.n_spec;
             const int64_t f0 = args.frame_begin + 4 * g + 2 * (T & 1);
             const FrameMeta m0 = locate_frame(args, f0, track);
             const FrameMeta m1 = locate_frame(args, f0 + 1, track);
@@ -563,170 +830,6 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
     if (warp == 0) tc::tmem_dealloc(tm, 512);
 }
 
-// ---------------- kernel B: filterbank + normalisation ----------------
-constexpr int kFbThreads = 128;
-constexpr int kFbTile = 64;                      // frames per tile: rows 0..63 = hi plane, 64..127 = lo plane
-constexpr int kFbKBlocks = kPlaneWords * 2 / 64; // 36 blocks of 64 bf16
-constexpr int kFbStages = 4;
-constexpr uint32_t kFbWBlk = 32 * 128;           // weights: 32 rows (12 hi + 4 zero | 12 lo + 4 zero) x 64 elements
-constexpr uint32_t kFbABlk = 128 * 128;
-constexpr uint32_t kSmemFb = kFbKBlocks * kFbWBlk + kFbStages * kFbABlk;     // 147 456 + 65 536
-
-struct FilterbankArgs {
-    const uint32_t *p_hi, *p_lo;
-    int64_t frame_begin, n_frames;               // chunk
-    const uint4 *w_img;                          // [36][4 KB]
-    const int64_t *frame_off, *out_off;
-    int n_tracks, normalize, out_f64;
-    void *out;
-};
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-
-__global__ void __launch_bounds__(kFbThreads, 1) chroma_tc_filterbank_kernel(const FilterbankArgs args)
-{
-    extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint32_t s_tmem;
-    __shared__ __align__(8) uint64_t s_free[kFbStages];
-    __shared__ __align__(8) uint64_t s_done;
-    __shared__ float s_part[kFbTile][kChroma];
-    const int tid = threadIdx.x;
-    const uint32_t lane_base = (uint32_t)(tid & ~31) << 16;
-    const uint32_t s_w = afs::smem_addr(smem), s_a = s_w + kFbKBlocks * kFbWBlk;
-    {
-        uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        for (int i = tid; i < (int)(kFbKBlocks * kFbWBlk / 16); i += kFbThreads) dst[i] = args.w_img[i];
-    }
-    if (tid == 0) {
-        for (int s = 0; s < kFbStages; s++) afs::mbar_init(&s_free[s], 1);
-        afs::mbar_init(&s_done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    tc::fence_async_smem();
-    if (tid < 32) tc::tmem_alloc(&s_tmem, 32);
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tm = s_tmem;
-    constexpr uint32_t idesc = tc::idesc_bf16_f32(128, 32);
-    const uint64_t w_desc = tc::smem_desc_k_sw128(s_w), a_desc = tc::smem_desc_k_sw128(s_a);
-
-    const int64_t n_tiles = (args.n_frames + kFbTile - 1) / kFbTile;
-    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total_blocks = my_tiles * kFbKBlocks;
-
-    // row `tid` of the A tile: frame (tid & 63) of the tile, plane hi (rows 0..63) or lo (rows 64..127)
-    auto issue_load = [&](int64_t seq) {
-        if (seq < total_blocks) {
-            const int64_t tile = blockIdx.x + (seq / kFbKBlocks) * gridDim.x;
-            const int kb = (int)(seq % kFbKBlocks);
-            const int64_t fl = tile * kFbTile + (tid & 63);
-            const bool ok = fl < args.n_frames;
-            const uint32_t *src = (tid < 64 ? args.p_hi : args.p_lo) + (ok ? fl : 0) * kPlaneWords + kb * 32;
-            const uint32_t dst = s_a + (uint32_t)(seq % kFbStages) * kFbABlk + (uint32_t)tid * 128;
-#pragma unroll
-            for (int c = 0; c < 8; c++) cp_async16(dst + ((uint32_t)(c ^ (tid & 7)) << 4), src + 4 * c, ok ? 16 : 0);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    for (int s = 0; s < kFbStages - 1; s++) issue_load(s);
-
-    uint32_t done_phase = 0;
-    for (int64_t seq = 0; seq < total_blocks; seq++) {
-        const int kb = (int)(seq % kFbKBlocks);
-        const int64_t tile = blockIdx.x + (seq / kFbKBlocks) * gridDim.x;
-        // this thread's output frame (rows 0..63): located while the loads are in flight
-        int track = 0;
-        int64_t m_idx = 0, frames_k = 0, o_base = 0;
-        bool ok_frame = false;
-        if (kb == 0 && tid < kFbTile) {
-            const int64_t fl = tile * kFbTile + tid;
-            ok_frame = fl < args.n_frames;
-            if (ok_frame) {
-                const int64_t f = args.frame_begin + fl;
-                int lo = 0, hi = args.n_tracks;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (args.frame_off[mid] <= f) lo = mid; else hi = mid;
-                }
-                track = lo;
-                m_idx = f - args.frame_off[track];
-                frames_k = args.frame_off[track + 1] - args.frame_off[track];
-                o_base = kChroma * args.out_off[track];
-            }
-            s_part[tid][0] = __int_as_float(track);            // parked in shared memory until the tile's epilogue
-            s_part[tid][1] = __int_as_float(ok_frame ? 1 : 0);
-        }
-        asm volatile("cp.async.wait_group %0;" ::"n"(kFbStages - 2) : "memory");
-        tc::fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-            const uint64_t ad = a_desc + (uint64_t)(((uint32_t)(seq % kFbStages) * kFbABlk) >> 4);
-            const uint64_t wd = w_desc + (uint64_t)(((uint32_t)kb * kFbWBlk) >> 4);
-#pragma unroll
-            for (int ks = 0; ks < 4; ks++) tc::mma_ss(tm, ad + 2 * ks, wd + 2 * ks, idesc, (kb | ks) != 0);
-            tc::mma_commit(&s_free[seq % kFbStages]);
-            if (kb == kFbKBlocks - 1) tc::mma_commit(&s_done);
-        }
-        // the stage that block seq + S - 1 goes into was last read by the MMAs of block seq - 1
-        if (seq >= 1) afs::mbar_wait(&s_free[(seq - 1) % kFbStages], (uint32_t)(((seq - 1) / kFbStages) & 1));
-        issue_load(seq + kFbStages - 1);
-        if (kb == kFbKBlocks - 1) {
-            afs::mbar_wait(&s_done, done_phase);
-            done_phase ^= 1u;
-            tc::fence_after_sync();
-            uint32_t va[16], vb[16];
-            tc::tmem_ld16(tm + lane_base, va);
-            tc::tmem_ld16(tm + lane_base + 16, vb);
-            tc::tmem_wait_ld();
-            int trk = 0, okf = 0;
-            if (tid < kFbTile) { trk = __float_as_int(s_part[tid][0]); okf = __float_as_int(s_part[tid][1]); }
-            __syncthreads();
-            if (tid >= kFbTile) {
-#pragma unroll
-                for (int c = 0; c < kChroma; c++) s_part[tid - kFbTile][c] = __uint_as_float(va[c]);      // P_lo . w_hi
-            }
-            __syncthreads();
-            if (tid < kFbTile && okf) {
-                float raw[kChroma];
-                float ss = 0.f;
-#pragma unroll
-                for (int c = 0; c < kChroma; c++) {
-                    raw[c] = (__uint_as_float(va[c]) + __uint_as_float(vb[c])) + s_part[tid][c];      // chroma.py:70 np.dot(chromafb, spec)
-                    ss = fmaf(raw[c], raw[c], ss);
-                }
-                float len = 1.f;
-                if (args.normalize) {
-                    // librosa.util.normalize(norm=2, axis=0), chroma.py:74: tiny lengths -> 1
-                    len = sqrtf(ss);
-                    if (len < FLT_MIN) len = 1.f;
-                }
-                const int64_t f = args.frame_begin + tile * kFbTile + tid;
-                const int64_t m = f - args.frame_off[trk];
-                const int64_t fk = args.frame_off[trk + 1] - args.frame_off[trk];
-                const int64_t ob = kChroma * args.out_off[trk] + m;
-#pragma unroll
-                for (int c = 0; c < kChroma; c++) {
-                    const float val = args.normalize ? raw[c] / len : raw[c];
-                    if (args.out_f64) static_cast<double *>(args.out)[ob + (int64_t)c * fk] = (double)val;
-                    else static_cast<float *>(args.out)[ob + (int64_t)c * fk] = val;
-                }
-            }
-            tc::fence_before_sync();
-            __syncthreads();          // accumulator and s_part are free for the next tile
-        }
-        (void)m_idx; (void)frames_k; (void)o_base;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    tc::fence_before_sync();
-    __syncthreads();
-    if (tid < 32) tc::tmem_dealloc(tm, 32);
-}
-
 uint16_t bf16_trunc(float x, float *back)
 {
     uint32_t u;
@@ -758,15 +861,16 @@ struct afs_chroma_tc {
     uint32_t *g_img = nullptr;
     float2 *tw = nullptr;
     float *hann = nullptr;
-    uint32_t *scratch = nullptr;      // [2 planes][chunk frames][kPlaneWords]
-    int64_t scratch_frames = 0;
-    int64_t chunk_frames = 16384;
+    uint32_t *ring = nullptr;         // power spectrum ring: [2 planes][ring_tiles * 64 frames][kPlaneWords]
+    int *flags = nullptr;             // [2][ring_tiles]: prod | cons
+    int ring_tiles = 48;              // 48 x 590 KB = 28 MB: stays in L2
+    int n_fb = 20;                    // CTAs that run the filterbank role
 };
 
 void chroma_tc_destroy(afs_chroma_tc *tc)
 {
     if (!tc) return;
-    cudaFree(tc->f_img); cudaFree(tc->w_img); cudaFree(tc->g_img); cudaFree(tc->tw); cudaFree(tc->hann); cudaFree(tc->scratch);
+    cudaFree(tc->f_img); cudaFree(tc->w_img); cudaFree(tc->g_img); cudaFree(tc->tw); cudaFree(tc->hann); cudaFree(tc->ring); cudaFree(tc->flags);
     delete tc;
 }
 
@@ -835,7 +939,7 @@ int chroma_tc_create(afs_chroma_tc **out, const std::vector<double> &fb, const s
             uint16_t hi, lo;
             bf16_split(fb[(size_t)k * kChroma + c], hi, lo);
             w_img[(size_t)kb * kFbWBlk / 2 + tc::sw128_offset(c, kk) / 2] = hi;
-            w_img[(size_t)kb * kFbWBlk / 2 + tc::sw128_offset(16 + c, kk) / 2] = lo;
+            w_img[(size_t)kb * kFbWBlk / 2 + tc::sw128_offset(12 + c, kk) / 2] = lo;
         }
     }
     for (int k = 0; k < kBins; k++)
@@ -855,14 +959,23 @@ int chroma_tc_create(afs_chroma_tc **out, const std::vector<double> &fb, const s
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chroma_tc_spectrum_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemA);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chroma_tc_spectrum_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemA);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chroma_tc_spectrum_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemA);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(chroma_tc_filterbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFb);
     if (e != cudaSuccess) {
         chroma_tc_destroy(tcp);
         return afs::fail(AFS_ERR_CUDA, "chroma_tc_create: %s", cudaGetErrorString(e));
     }
-    if (const char *c = getenv("AFS_CHROMA_TC_CHUNK")) {
-        const long long v = atoll(c);
-        if (v >= 64) tcp->chunk_frames = (v + 63) / 64 * 64;
+    if (const char *c = getenv("AFS_CHROMA_TC_RING")) {
+        const int v = atoi(c);
+        if (v >= 2) tcp->ring_tiles = v;
+    }
+    if (const char *c = getenv("AFS_CHROMA_TC_FB")) {
+        const int v = atoi(c);
+        if (v >= 1 && v < afs::sm_count()) tcp->n_fb = v;
+    }
+    cudaError_t e2 = cudaMalloc(&tcp->ring, sizeof(uint32_t) * 2 * (size_t)tcp->ring_tiles * kFbTile * kPlaneWords);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&tcp->flags, sizeof(int) * 2 * tcp->ring_tiles);
+    if (e2 != cudaSuccess) {
+        chroma_tc_destroy(tcp);
+        return afs::fail(AFS_ERR_CUDA, "chroma_tc_create: %s", cudaGetErrorString(e2));
     }
     *out = tcp;
     return AFS_OK;
@@ -870,81 +983,65 @@ int chroma_tc_create(afs_chroma_tc **out, const std::vector<double> &fb, const s
 
 int chroma_tc_run(afs_chroma_tc *tcp, const ChromaBatch &bt, cudaStream_t st)
 {
-    const int64_t chunk = tcp->chunk_frames < bt.total_frames ? tcp->chunk_frames : (bt.total_frames + 63) / 64 * 64;
-    if (tcp->scratch_frames < chunk) {
-        // grow-only scratch for the power spectrum of one chunk (stream-ordered use: one batch at a time per plan)
-        AFS_CUDA(cudaStreamSynchronize(st));
-        cudaFree(tcp->scratch);
-        tcp->scratch = nullptr;
-        tcp->scratch_frames = 0;
-        AFS_CUDA(cudaMalloc(&tcp->scratch, sizeof(uint32_t) * 2 * (size_t)chunk * kPlaneWords));
-        tcp->scratch_frames = chunk;
-    }
+    // One launch for the whole batch: CTAs [0, n_fb) run the filterbank role, the others the spectrum role; both are
+    // persistent and every CTA is resident (grid <= number of SMs, one CTA per SM), which the hand-off through the
+    // power-spectrum ring relies on.
+    if (bt.total_frames <= 0) return AFS_OK;
     const int n_sm = afs::sm_count();
-    for (int64_t f0 = 0; f0 < bt.total_frames; f0 += chunk) {
-        const int64_t f1 = f0 + chunk < bt.total_frames ? f0 + chunk : bt.total_frames;
-        SpectrumArgs sa;
-        sa.audio = bt.audio;
-        sa.sample_off = bt.sample_off;
-        sa.frame_off = bt.frame_off;
-        sa.n_tracks = bt.n_tracks;
-        sa.frame_begin = f0;
-        sa.frame_end = f1;
-        sa.hop = bt.hop;
-        sa.center_pad = bt.center_pad;
-        sa.f_img = tcp->f_img;
-        sa.g_img = tcp->g_img;
-        sa.tw = tcp->tw;
-        sa.hann = tcp->hann;
-        sa.p_hi = tcp->scratch;
-        sa.p_lo = tcp->scratch + (size_t)tcp->scratch_frames * kPlaneWords;
-        sa.trace = nullptr;
-        // AFS_CHROMA_TC_TRACE=<file>: clock64 stamps of every warp's pipeline events in the first chunk (debugging aid)
-        const char *trace_path = f0 == 0 ? getenv("AFS_CHROMA_TC_TRACE") : nullptr;
-        const size_t trace_n = (size_t)n_sm * (kThreadsA / 32) * kTraceLen;
-        if (trace_path) {
-            AFS_CUDA(cudaMalloc(&sa.trace, trace_n * sizeof(long long)));
-            AFS_CUDA(cudaMemsetAsync(sa.trace, 0, trace_n * sizeof(long long), st));
+    const int64_t groups = (bt.total_frames + 3) / 4, tiles = (bt.total_frames + kFbTile - 1) / kFbTile;
+    SpectrumArgs sa;
+    sa.audio = bt.audio;
+    sa.sample_off = bt.sample_off;
+    sa.frame_off = bt.frame_off;
+    sa.n_tracks = bt.n_tracks;
+    sa.frame_begin = 0;
+    sa.frame_end = bt.total_frames;
+    sa.hop = bt.hop;
+    sa.center_pad = bt.center_pad;
+    sa.f_img = tcp->f_img;
+    sa.g_img = tcp->g_img;
+    sa.tw = tcp->tw;
+    sa.hann = tcp->hann;
+    sa.ring_tiles = tcp->ring_tiles;
+    sa.p_hi = tcp->ring;
+    sa.p_lo = tcp->ring + (size_t)tcp->ring_tiles * kFbTile * kPlaneWords;
+    sa.prod = tcp->flags;
+    sa.cons = tcp->flags + tcp->ring_tiles;
+    sa.n_fb = (int)(tiles < tcp->n_fb ? tiles : tcp->n_fb);
+    sa.n_spec = (int)(groups < n_sm - sa.n_fb ? groups : n_sm - sa.n_fb);
+    sa.w_img = tcp->w_img;
+    sa.out_off = bt.out_off;
+    sa.normalize = bt.normalize;
+    sa.out_f64 = bt.out_f64;
+    sa.out = bt.out;
+    sa.trace = nullptr;
+    AFS_CUDA(cudaMemsetAsync(tcp->flags, 0, sizeof(int) * 2 * tcp->ring_tiles, st));
+    // AFS_CHROMA_TC_TRACE=<file>: clock64 stamps of every warp's pipeline events (debugging aid)
+    const char *trace_path = getenv("AFS_CHROMA_TC_TRACE");
+    const size_t trace_n = (size_t)n_sm * (kThreadsA / 32) * kTraceLen;
+    if (trace_path) {
+        AFS_CUDA(cudaMalloc(&sa.trace, trace_n * sizeof(long long)));
+        AFS_CUDA(cudaMemsetAsync(sa.trace, 0, trace_n * sizeof(long long), st));
+    }
+    const unsigned blocks = (unsigned)(sa.n_fb + sa.n_spec);
+    if (sa.trace) {
+        if (bt.pcm16) chroma_tc_spectrum_kernel<true, true><<<blocks, kThreadsA, kSmemA, st>>>(sa);
+        else chroma_tc_spectrum_kernel<false, true><<<blocks, kThreadsA, kSmemA, st>>>(sa);
+    } else if (bt.pcm16) chroma_tc_spectrum_kernel<true, false><<<blocks, kThreadsA, kSmemA, st>>>(sa);
+    else chroma_tc_spectrum_kernel<false, false><<<blocks, kThreadsA, kSmemA, st>>>(sa);
+    afs::count_launch();
+    AFS_CUDA(cudaGetLastError());
+    if (trace_path) {
+        std::vector<long long> host(trace_n);
+        AFS_CUDA(cudaMemcpyAsync(host.data(), sa.trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        AFS_CUDA(cudaStreamSynchronize(st));
+        cudaFree(sa.trace);
+        if (FILE *fp = fopen(trace_path, "wb")) {
+            const int hdr[4] = {n_sm, kThreadsA / 32, kTraceLen, sa.n_spec};
+            fwrite(hdr, sizeof(int), 4, fp);
+            fwrite(host.data(), sizeof(long long), trace_n, fp);
+            fclose(fp);
         }
-        const int64_t groups = (f1 - f0 + 3) / 4;
-        int64_t blocks = groups;
-        if (blocks > n_sm) blocks = n_sm;
-        if (sa.trace) {
-            if (bt.pcm16) chroma_tc_spectrum_kernel<true, true><<<(unsigned)blocks, kThreadsA, kSmemA, st>>>(sa);
-            else chroma_tc_spectrum_kernel<false, true><<<(unsigned)blocks, kThreadsA, kSmemA, st>>>(sa);
-        } else if (bt.pcm16) chroma_tc_spectrum_kernel<true, false><<<(unsigned)blocks, kThreadsA, kSmemA, st>>>(sa);
-        else chroma_tc_spectrum_kernel<false, false><<<(unsigned)blocks, kThreadsA, kSmemA, st>>>(sa);
-        afs::count_launch();
-        AFS_CUDA(cudaGetLastError());
-        if (trace_path) {
-            std::vector<long long> host(trace_n);
-            AFS_CUDA(cudaMemcpyAsync(host.data(), sa.trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost, st));
-            AFS_CUDA(cudaStreamSynchronize(st));
-            cudaFree(sa.trace);
-            if (FILE *fp = fopen(trace_path, "wb")) {
-                const int hdr[4] = {n_sm, kThreadsA / 32, kTraceLen, (int)blocks};
-                fwrite(hdr, sizeof(int), 4, fp);
-                fwrite(host.data(), sizeof(long long), trace_n, fp);
-                fclose(fp);
-            }
-        }
-        FilterbankArgs fa;
-        fa.p_hi = sa.p_hi;
-        fa.p_lo = sa.p_lo;
-        fa.frame_begin = f0;
-        fa.n_frames = f1 - f0;
-        fa.w_img = tcp->w_img;
-        fa.frame_off = bt.frame_off;
-        fa.out_off = bt.out_off;
-        fa.n_tracks = bt.n_tracks;
-        fa.normalize = bt.normalize;
-        fa.out_f64 = bt.out_f64;
-        fa.out = bt.out;
-        int64_t tiles = (f1 - f0 + kFbTile - 1) / kFbTile;
-        if (tiles > n_sm) tiles = n_sm;
-        chroma_tc_filterbank_kernel<<<(unsigned)tiles, kFbThreads, kSmemFb, st>>>(fa);
-        afs::count_launch();
-        AFS_CUDA(cudaGetLastError());
     }
     return AFS_OK;
 }
