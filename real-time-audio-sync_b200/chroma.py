@@ -7,7 +7,7 @@ and the L2 normalisation run fused in kernel K1 (csrc/chroma.cu) through
 ``afs_chroma_batch``; WAV decoding stays on the CPU (it only feeds samples).
 
 Differences from the reference, all explicit:
-* three arithmetic modes: ``compute="fp32"`` (default) runs the DFT as two matrix products on the
+* three arithmetic modes: ``compute="tc"`` (default) runs the DFT as two matrix products on the
   tensor cores with bf16x3 split operands and fp32 accumulation (<= 2e-5 abs from the float64
   reference on normalised chroma); ``"fp32"`` is the CUDA-core FFT kernel in float32 (<= 1e-6);
   ``"fp64"`` the same kernel in float64 (<= 1e-9);
@@ -83,7 +83,7 @@ class ChromaPlan(object):
     def num_frames(self, n_samples, center=True):
         return int(nat.lib().afs_chroma_num_frames(self._h, int(n_samples), 1 if center else 0))
 
-    def run(self, d_audio, offsets, d_out=None, center=True, normalize=True, out_dtype=torch.float32, compute="fp32",
+    def run(self, d_audio, offsets, d_out=None, center=True, normalize=True, out_dtype=torch.float32, compute="tc",
             out_offsets=None):
         """K1 on the current stream.  d_audio: float32 device tensor holding all tracks, or int16 PCM
         (sample = value / 32768 as librosa.load scales WAV data; converted inside the kernel);
@@ -132,7 +132,7 @@ def default_plan():
     return _default_plan
 
 
-def chroma_batch(tracks, center=True, normalize=True, compute="fp32"):
+def chroma_batch(tracks, center=True, normalize=True, compute="tc"):
     """Many tracks in one launch: list of 1-D sample arrays -> list of (12, frames) float64 arrays."""
     plan = default_plan()
     # int16 tracks (raw PCM, see load_wav_pcm16) travel and are staged as int16; anything else as float32
@@ -156,7 +156,7 @@ def chroma_batch(tracks, center=True, normalize=True, compute="fp32"):
     return outs
 
 
-def wav_samples_to_chroma(wav, normalize=True, compute="fp32"):
+def wav_samples_to_chroma(wav, normalize=True, compute="tc"):
     """create_chroma(create_stft(wav)) (chroma.py:31-33) -> (12, M) float64."""
     return chroma_batch([np.asarray(wav)], center=True, normalize=normalize, compute=compute)[0]
 
@@ -194,7 +194,7 @@ def wav_to_chroma(path_to_wav):
     return wav_samples_to_chroma(pcm)
 
 
-def wav_to_chroma_col(wav_buf, compute="fp32"):
+def wav_to_chroma_col(wav_buf, compute="tc"):
     """chroma.py:35-42: one un-padded 4096-sample frame -> (12,)."""
     assert(len(wav_buf) == fft_len)
     return chroma_batch([np.asarray(wav_buf)], center=False, compute=compute)[0][:, 0]

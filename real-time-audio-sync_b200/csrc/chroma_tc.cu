@@ -13,19 +13,23 @@
 // (hi*hi + lo*hi + hi*lo): measured 1.2e-5 worst absolute error on normalised chroma of real audio against the
 // float64 reference (tolerance 1e-4), independent of the signal's scale (bf16 keeps the float32 exponent).
 //
-// Kernel A (chroma_tc_spectrum_kernel), one CTA per SM, two independent 256-thread pipelines per CTA that run the
-// same sequential program on alternate groups of 4 frames — while one waits for its MMAs the other converts,
-// twiddles or squares, so the tensor pipe and the CUDA cores overlap without any cross-pipeline synchronisation:
-//   convert   thread (frame, n2) loads its 64 samples x[64 n1 + n2] (coalesced across n2), applies the window, splits,
-//             and stores them as the K-major A operand [128 rows = 2 frames x 64 n2][K = n1] (128-byte swizzle)
-//   MMA 1     D1[(f, n2)][64] = A1 . F^T     (12 MMAs, N = 64: Re Y[0], Re Y[32], then Re/Im Y[k1], k1 = 1..31)
-//   epilogue1 tcgen05.ld, twiddle in registers (the thread's n2 is fixed, so its twiddles are too), split, store as
-//             the B operand of stage 2: row (frame, k1), K = (n2, re/im)
-//   MMA 2     D2[(k2, re/im)][(frame, k1)] = G . Y'^T   (24 MMAs, N = 144; G lives in TMEM as the A operand)
-//   epilogue2 squares; re^2 + im^2 meet through one shuffle between neighbouring lanes; split; the power spectrum
-//             goes to a scratch buffer as two bf16 planes (L2 resident: the host runs the batch in chunks)
-// Kernel B (chroma_tc_filterbank_kernel): [64 frames x (hi | lo) planes] x [bins x 12] as tcgen05.mma with the weight
-// matrix resident in shared memory, then L2 normalisation and the feature-major store.
+// One persistent launch (chroma_tc_spectrum_kernel), one CTA per SM, two kinds of CTA:
+//  * spectrum CTAs (all but 16): groups of 4 frames flow through warp-specialised roles that only meet through mbarriers
+//      L   TMA bulk copies of the audio into a shared-memory ring (the memory system answers after ~1.6 us, so ~50 KB per
+//          SM have to be in flight; overlapping frames share the hop they have in common)
+//      C   samples x window -> bf16 hi/lo -> A operand of stage 1, written straight into TMEM (tcgen05.st)
+//      M   one elected lane issues every tcgen05.mma:  D1[(f, n2)][64] = A1 . F^T   (12 MMAs per 2 frames, N = 64),
+//          D2[(k2, re/im)][(frame, k1)] = G . Y'^T   (24 MMAs per 4 frames, N = 144; G lives in TMEM as the A operand)
+//      E1  tcgen05.ld of D1, twiddle in registers (the thread's n2 is fixed, so its twiddles are too), split, store as the
+//          B operand of stage 2 in shared memory: row (frame, k1), K = (n2, re/im)
+//      E2  tcgen05.ld of D2, squares; re^2 + im^2 meet through one shuffle between neighbouring lanes; split; the power
+//          spectrum goes to a ring in global memory (28 MB, L2 resident) already laid out as the next MMA's A operand
+//      P   publishes stored groups to the filterbank CTAs (gpu-scope release) and checks that ring slots are free again
+//  * filterbank CTAs (16): [64 frames x (hi | lo) planes] x [bins x 12] as tcgen05.mma with the weight matrix resident
+//    in shared memory and the power spectrum streamed in by TMA bulk copies, then L2 normalisation and the
+//    feature-major store.
+// What bounds it (profiles/README.md): the CUDA-core work around the MMAs — 3 500 warp instructions per frame, a quarter
+// of them the bf16 hi/lo splits — not the tensor pipe (720 cycles per frame) and not HBM.
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
@@ -864,7 +868,7 @@ struct afs_chroma_tc {
     uint32_t *ring = nullptr;         // power spectrum ring: [2 planes][ring_tiles * 64 frames][kPlaneWords]
     int *flags = nullptr;             // [2][ring_tiles]: prod | cons
     int ring_tiles = 48;              // 48 x 590 KB = 28 MB: stays in L2
-    int n_fb = 20;                    // CTAs that run the filterbank role
+    int n_fb = 16;                    // CTAs that run the filterbank role
 };
 
 void chroma_tc_destroy(afs_chroma_tc *tc)
