@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--length", type=int, default=DTW_LEN)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--chroma-tracks", type=int, default=CHROMA_TRACKS)
+    ap.add_argument("--chroma-compute", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--otw-streams", type=int, default=OTW_STREAMS)
     ap.add_argument("--otw-steps", type=int, default=0)
     ap.add_argument("--wtw-streams", type=int, default=1024)
@@ -259,6 +260,24 @@ def main():
             if k != head_key:
                 line[k] = v
         line["clocks"] = clocks
+        # the figures of the other workloads once more as flat scalars, so that they survive any post-processing that keeps
+        # only the top level of the line
+        def pick(key, *path):
+            o = results.get(key)
+            for k in path:
+                o = o.get(k) if isinstance(o, dict) else None
+            return o
+        line["chroma_frames_per_s"] = pick("chroma", "value")
+        line["chroma_hbm_frac"] = pick("chroma", "roofline", "frac")
+        line["chroma_e2e_frames_per_s"] = pick("chroma", "e2e", "value")
+        line["otw_p99_ms"] = pick("otw", "value")
+        line["otw_p50_ms"] = pick("otw", "ms_per_step")
+        line["wtw_value"] = pick("wtw", "value")
+        line["striped_gcups"] = pick("striped", "value")
+        line["striped_ms"] = pick("striped", "ms_per_step")
+        line["striped_single_gpu_ms"] = pick("striped", "single_gpu_ms")
+        line["striped_parity"] = pick("striped", "parity_vs_single_gpu")
+        line["dtw_weak_gcups"] = pick("dtw", "weak", "value")
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -333,13 +352,67 @@ def bench_striped(ctx):
     if rank == 0:
         d = np.diff(path, axis=0)
         ok = bool(path[0].tolist() == [0, 0] and path[-1].tolist() == [n - 1, n - 1] and ((d >= 0) & (d <= 1)).all() and (d.sum(axis=1) >= 1).all())
+        # the same pair un-striped on this one GPU (K2 + K3; the direction map of n x n cells is n^2 / 4 bytes): the striped
+        # result must be bit-equal — accumulated cost at the end cell and every path point — and it is the time to beat
+        single = {"parity_vs_single_gpu": None, "single_gpu_ms": None}
+        try:
+            dtw = g.submodule("dtw")
+            free_b = torch.cuda.mem_get_info()[0]
+            if float(n) * n / 4 * 1.15 < free_b:
+                plan1 = dtw.DtwPlan([n], [n], dtype="fp64")
+                d_b_full = torch.from_numpy(b).cuda()
+                plan1.accumulate(d_a, d_b_full)
+                plan1.backtrack()
+                torch.cuda.synchronize()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                plan1.accumulate(d_a, d_b_full)
+                s1.record()
+                plan1.backtrack()
+                torch.cuda.synchronize()
+                end1 = float(plan1.acc_end.cpu()[0])
+                st1, ln1 = int(plan1.path_start.cpu()[0]), int(plan1.path_len.cpu()[0])
+                path1 = plan1.path[st1 : st1 + ln1].cpu().numpy().astype(np.int64)
+                same = bool(end1 == float(end.item()) and path1.shape == path.shape and np.array_equal(path1, path))
+                single = {"parity_vs_single_gpu": same, "single_gpu_ms": s0.elapsed_time(s1), "single_gpu_acc_end": end1}
+                plan1.close()
+                del d_b_full
+            else:
+                single["note"] = "pair too large for one GPU's direction map"
+        except Exception as exc:
+            single["error"] = repr(exc)[:200]
         out = {"metric": "striped_dtw_gcups", "value": float(n) * n / t_acc / 1e9, "unit": "GCUPS", "n_gpus": world,
                "ms_per_step": t_acc * 1e3, "backtrack_ms": t_bt * 1e3, "scaling": "weak (25k columns per GPU)", "dtype": "f64",
                "config": {"workload": "single %d x %d pair column-striped over %d GPUs, NVLink peer-store boundary hand-off (BASELINE cfg[4] at 8 GPUs)" % (n, n, world)},
                "acc_end": float(end.item()), "path_len": int(len(path)), "path_valid": ok,
                "note": "a single pair is bound by the wavefront's critical path (bands x 64-step lag + columns), not by aggregate throughput"}
+        out.update(single)
     sd.close()
     return out
+
+
+def load_traffic(kernel, config):
+    """DRAM bytes per launch of `kernel` at `config` from profiles/traffic.json (written by tools/make_traffic_json.py from
+    an `ncu --set full` capture).  An entry records the SHA-1 of the kernel's source files at capture time: if a source
+    has changed since, the figure is stale and None is reported instead."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            entries = json.load(fh)["entries"]
+    except Exception:
+        return None, "profiles/traffic.json missing"
+    for e in entries:
+        if e.get("kernel") == kernel and e.get("config") == config:
+            for rel, sha in e.get("src_sha1", {}).items():
+                try:
+                    with open(os.path.join(ROOT, rel), "rb") as fh:
+                        now = hashlib.sha1(fh.read()).hexdigest()
+                except OSError:
+                    now = None
+                if now != sha:
+                    return None, "stale: %s changed since the capture %s" % (rel, e.get("source"))
+            return float(e["dram_bytes"]), e.get("source")
+    return None, "no capture for this kernel / configuration"
 
 
 def load_peaks():
@@ -354,7 +427,9 @@ def bench_dtw(ctx):
     args, rank, world, torch, nat, g = ctx["args"], ctx["rank"], ctx["world"], ctx["torch"], ctx["nat"], ctx["g"]
     barrier, max_over_ranks = ctx["barrier"], ctx["max_over_ranks"]
     dtw = g.submodule("dtw")
-    P, Ln = args.pairs, args.length
+    # BASELINE cfg[2] as worded: ONE batch of 256 pairs, sharded over the ranks (strong scaling: 256 / N pairs per rank)
+    P_total, Ln = args.pairs, args.length
+    P = max(1, P_total // world)
     live, ref = synth_chroma_pairs(P, Ln, 2000 + rank * P)
     npdt = np.float64 if args.dtype == "fp64" else np.float32
     h_a = torch.from_numpy(np.ascontiguousarray(live, dtype=npdt)).pin_memory()
@@ -385,8 +460,46 @@ def bench_dtw(ctx):
     acc_ms = [e[0].elapsed_time(e[1]) for e in ev]
     bt_ms = [e[1].elapsed_time(e[2]) for e in ev]
     step_ms = float(np.mean(acc_ms) + np.mean(bt_ms))
-    step_ms_max = max_over_ranks(step_ms)
     cells_rank = float(plan.cells)
+    step_mode = "one step at a time on one stream (256 MiB L2 flush between steps)"
+    if 2 * P <= DTW_PAIRS_PER_GPU:
+        # A rank's share is a fraction of the batch: a launch of few pairs spends ~6 ms of its ~20 filling and draining the
+        # chain of bands, so consecutive steps alternate between two plans on two streams and the next step's bands fill the
+        # SMs the previous one vacates.  Every step is still a full accumulate + backtrack of the rank's pairs; the timed
+        # region is K steps between one start event and the later of the two streams' end events.
+        plan_b = dtw.DtwPlan([Ln] * P, [Ln] * P, dtype=args.dtype)
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        plans = [plan, plan_b]
+
+        def run_steps(k_steps):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for st in streams:
+                st.wait_event(e0)
+            for k in range(k_steps):
+                with torch.cuda.stream(streams[k & 1]):
+                    plans[k & 1].accumulate(d_a, d_b)
+                    plans[k & 1].backtrack()
+            ends = []
+            for st in streams:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record(st)
+                ends.append(e1)
+            torch.cuda.synchronize()
+            return max(e0.elapsed_time(e1) for e1 in ends)
+
+        run_steps(2)
+        barrier()
+        launches0 = nat.launch_count()
+        total_ms = run_steps(args.steps)
+        barrier()
+        launches = nat.launch_count() - launches0
+        step_ms = total_ms / args.steps
+        step_mode = ("steps alternate between two plans on two streams (the next step's bands fill the SMs the previous step "
+                     "vacates); no L2 flush: a step writes %.1f GB of direction map, far more than the 126 MB L2" % (cells_rank / 4 / 1e9))
+        plan_b.close()
+        del plan_b
+    step_ms_max = max_over_ranks(step_ms)
     value = cells_rank * world / (step_ms_max * 1e-3) / 1e9
 
     # ---- e2e: host (pinned) buffers in, paths out, through the plan object the drop-in API uses ----
@@ -441,6 +554,28 @@ def bench_dtw(ctx):
     del pipe
     h2d = int(h_a.numel() * h_a.element_size() + h_b.numel() * h_b.element_size())
     d2h = int(h_path.numel() * 4 + h_start.numel() * 4 + h_len.numel() * 4 + h_end.numel() * 8)
+    # ---- weak-scaling companion (N > 1): the full batch on every GPU, as round 1 reported it ----
+    weak = None
+    if world > 1 and P < P_total and P_total % P == 0:
+        rep = P_total // P
+        wa, wb = d_a.repeat(rep, 1, 1), d_b.repeat(rep, 1, 1)
+        wplan = dtw.DtwPlan([Ln] * P_total, [Ln] * P_total, dtype=args.dtype)
+        wplan.accumulate(wa, wb)
+        wplan.backtrack()
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for _ in range(2):
+            wplan.accumulate(wa, wb)
+            wplan.backtrack()
+        w1.record()
+        barrier()
+        wms = max_over_ranks(w0.elapsed_time(w1) / 2)
+        weak = {"value": float(wplan.cells) * world / (wms * 1e-3) / 1e9, "unit": "GCUPS", "scaling": "weak", "pairs_per_gpu": P_total,
+                "ms_per_step": wms, "steps": 2, "note": "%d pairs on every GPU (the rank's %d pairs repeated)" % (P_total, P)}
+        wplan.close()
+        del wplan, wa, wb
+        torch.cuda.empty_cache()
     # ---- the other arithmetic mode on the same data (kernel only): fp32 offsets against fp64 bases ----
     other = None
     if args.dtype == "fp64":
@@ -473,6 +608,7 @@ def bench_dtw(ctx):
     achieved_tflops = cells_rank * DTW_FLOP_PER_CELL / (acc_ms_mean * 1e-3) / 1e12
     alg_bytes = cells_rank * 0.25 + 2 * P * 12 * Ln * (8 if args.dtype == "fp64" else 4)
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    dtw_traffic = load_traffic("dtw_wavefront_kernel<%s>" % ("double" if args.dtype == "fp64" else "float"), "%dx%d" % (P, Ln))
     roofline = {
         "kernel": "dtw_wavefront_kernel<%s>" % ("double" if args.dtype == "fp64" else "float"),
         "bound": "fp64_pipe" if args.dtype == "fp64" else "fp32_pipe",
@@ -489,21 +625,21 @@ def bench_dtw(ctx):
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at exactly this configuration; None for any other.
         # 256 pairs: the packed seq_b of all pairs (573 MB) no longer fits L2, so the per-band re-reads of seq_b reach DRAM
         # (80.7 GB read + 37.3 GB written; 0.76 TB/s = 12 % of the HBM peak, not limiting: see DESIGN.md K2).
-        "traffic": {(256, 20000): 118.05e9, (32, 20000): 4.852e9}.get((P, Ln)) if args.dtype == "fp64" else None,
-        "traffic_source": "profiles/ncu_raw_r1n_dtw.csv (256 pairs) / ncu_raw_r1j_dtw.csv (32 pairs): ncu --set full of the same launch",
+        "traffic": dtw_traffic[0], "traffic_source": dtw_traffic[1],
         "algorithmic_bytes": alg_bytes,
     }
     cpu = None if args.no_cpu_baseline else cpu_dtw_baseline(seconds=args.cpu_seconds)
     return {
         "metric": "dtw_gcups", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup_effective, "ms_per_step": step_ms_max, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup_effective, "ms_per_step": step_ms_max, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64" if args.dtype == "fp64" else "f32", "data": "synthetic",
-        "config": {"workload": "offline full DTW %dx%d chroma frames, batch of %d pairs per GPU (BASELINE cfg[2] in full on every GPU; weak scaling)" % (Ln, Ln, P),
-                   "pairs_per_gpu": P, "frames": Ln, "features": 12,
-                   "l2": "256 MiB flush between timed steps; per-step working set 3.2 GB direction map > 126 MB L2",
-                   "step": "accumulate (K2) + backtrack (K3)", "parallelism": "pairs sharded over ranks, no collective"},
+        "config": {"workload": "offline full DTW %dx%d chroma frames, one batch of %d pairs sharded over %d GPU(s): %d pairs per GPU (BASELINE cfg[2]; strong scaling)" % (Ln, Ln, P * world, world, P),
+                   "pairs_total": P * world, "pairs_per_gpu": P, "frames": Ln, "features": 12,
+                   "l2": "per-step working set %.1f GB of direction map per GPU > 126 MB L2" % (cells_rank / 4 / 1e9),
+                   "step": "accumulate (K2) + backtrack (K3)", "step_mode": step_mode,
+                   "parallelism": "pairs sharded over ranks, no collective"},
         "kernel_ms": {"accumulate": acc_ms_mean, "backtrack": float(np.mean(bt_ms))},
-        "fp32_mode": other,
+        "fp32_mode": other, "weak": weak,
         "wall_s_timed_region": t_wall,
         "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": 2 * e2e_steps,
                 "mode": "dtw.DtwPipeline(depth=2): a stream of batches, two in flight on two plans / compute streams; a batch's "
@@ -576,20 +712,21 @@ def bench_chroma(ctx):
     T = args.chroma_tracks
     n = int(CHROMA_SECONDS * 22050)            # 6 615 000 samples
     plan = ch.default_plan()
+    compute = args.chroma_compute          # "tc": tcgen05 DFT-as-GEMM pipeline (default); "fp32": CUDA-core FFT kernel
     audio = synth_audio_tracks(torch, T, n, 1000 + rank, "cuda").reshape(-1)
     offs = np.arange(T + 1, dtype=np.int64) * n
-    out, foffs = plan.run(audio, offs)
+    out, foffs = plan.run(audio, offs, compute=compute)
     frames = int(foffs[-1])
     steps = args.steps
     for _ in range(args.warmup_effective):
-        plan.run(audio, offs, d_out=out)
+        plan.run(audio, offs, d_out=out, compute=compute)
     barrier()
     launches0 = nat.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
     for k in range(steps):
         ev[k][0].record()
-        plan.run(audio, offs, d_out=out)          # input 27 GB per step >> 126 MB L2: no flush needed
+        plan.run(audio, offs, d_out=out, compute=compute)          # input 27 GB per step >> 126 MB L2: no flush needed
         ev[k][1].record()
     barrier()
     launches = nat.launch_count() - launches0
@@ -617,7 +754,7 @@ def bench_chroma(ctx):
                 ready = torch.cuda.Event()
                 ready.record(copy_stream)
             torch.cuda.current_stream().wait_event(ready)
-            plan.run(d_bufs[b], slab_offs, d_out=d_outs[b])
+            plan.run(d_bufs[b], slab_offs, d_out=d_outs[b], compute=compute)
             h_out[i].copy_(d_outs[b], non_blocking=True)
             done = torch.cuda.Event()
             done.record()
@@ -645,12 +782,12 @@ def bench_chroma(ctx):
         h_pcm = (h_slab * 32768.0).round().clamp_(-32768, 32767).to(torch.int16).pin_memory()
         d_pcm = [torch.empty(slab_tracks * n, dtype=torch.int16, device="cuda") for _ in range(2)]
         e2e_pcm = time_e2e(h_pcm, d_pcm, 2, "int16 PCM samples on the host (afs_chroma_batch_pcm16)")
-        plan.run(d_pcm[0], slab_offs, d_out=d_outs[0])
+        plan.run(d_pcm[0], slab_offs, d_out=d_outs[0], compute=compute)
         torch.cuda.synchronize()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
         for _ in range(3):
-            plan.run(d_pcm[0], slab_offs, d_out=d_outs[0])
+            plan.run(d_pcm[0], slab_offs, d_out=d_outs[0], compute=compute)
         p1.record()
         torch.cuda.synchronize()
         pcm_resident = {"value": frames_slab * 3 / (p0.elapsed_time(p1) * 1e-3), "unit": "frames/s per GPU",
@@ -665,6 +802,8 @@ def bench_chroma(ctx):
     gbs = frames * CHROMA_BYTES_PER_FRAME / (ms * 1e-3) / 1e9
     tfl = frames * CHROMA_FLOP_PER_FRAME / (ms * 1e-3) / 1e12
     cpu = None if args.no_cpu_baseline else cpu_chroma_baseline(seconds=min(8.0, args.cpu_seconds))
+    kernel_name = "chroma_tc_spectrum_kernel" if compute == "tc" else "chroma_fast_kernel<17>"
+    ch_tr = load_traffic(kernel_name, "per frame")
     return {
         "metric": "chroma_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps,
         "warmup": args.warmup_effective, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
@@ -672,11 +811,12 @@ def bench_chroma(ctx):
         "config": {"workload": "batched chroma extraction: %d synthetic 5-min 22.05 kHz tracks per GPU, n_fft=4096, hop=2048 (BASELINE cfg[1])" % T,
                    "tracks_per_gpu": T, "frames_per_step": frames, "l2": "27 GB of input per step >> 126 MB L2"},
         "e2e": e2e, "e2e_pcm16": e2e_pcm, "pcm16_resident": pcm_resident, "gpu_launches": int(launches),
-        "roofline": {"kernel": "chroma_fast_kernel<17>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+        "compute": compute,
+        "roofline": {"kernel": kernel_name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": gbs / hbm_peak, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
-                     "bytes_per_frame": CHROMA_BYTES_PER_FRAME,
-                     # ncu: 346.5 MB of DRAM traffic for a 41 344-frame launch = 8382 B/frame (algorithmic 8240)
-                     "traffic": 8382.0 * frames, "traffic_source": "profiles/ncu_raw_r1m_chroma.csv (346.5 MB for 41 344 frames), per frame x frames",
+                     "bytes_per_frame": CHROMA_BYTES_PER_FRAME, "kernel_ms": ms,
+                     "traffic": None if ch_tr[0] is None else ch_tr[0] * frames, "traffic_source": ch_tr[1],
+                     "traffic_note": "capture of a smaller launch of the same kernel, DRAM bytes per frame x frames of this launch",
                      "fp32": {"achieved": tfl, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tfl / fp32_peak,
                               "flop_per_frame": CHROMA_FLOP_PER_FRAME,
                               "peak_source": "derived: %d SMs x 128 lanes x 2 x %.0f MHz" % (n_sm, sm_max)}},
@@ -809,12 +949,15 @@ def bench_otw(ctx):
     # The reference and live windows (c x 96 B each) are re-read every step and do not fit L2 for 4096 streams.
     # ncu --set full of ONE heavy step (t = 703, all 4096 streams run a row sweep and a column sweep): 1.03 GB read +
     # 0.06 GB written.  It is set against the live p99 kernel time (the heavy steps), not the mean.
-    traffic = 1.096e9 * S / 4096.0
+    # Algorithmic bytes of a heavy step: every stream re-reads its reference and live windows, c columns x 96 B each
+    # (2 x 500 x 96 B x 4096 streams = 0.39 GB), and they do not fit L2.  Set against the live p99 kernel time (the heavy steps).
+    alg = 2.0 * OTW_C * 96 * S
     heavy_ms = o["kernel_ms_p99"]
-    otw_roof = {"kernel": "otw_step_kernel", "bound": "hbm", "achieved": traffic / (heavy_ms * 1e-3) / 1e9,
-                "peak": hbm_peak, "unit": "GB/s", "frac": traffic / (heavy_ms * 1e-3) / 1e9 / hbm_peak,
-                "peak_source": "measured" if "hbm_gbs" in peaks else "fallback", "traffic": traffic, "kernel_ms": heavy_ms,
-                "traffic_source": "profiles/ncu_raw_r1m_otw.csv (one heavy step, 4096 streams), scaled by stream count; time = live p99 kernel time",
+    tr, tr_src = load_traffic("otw_step_kernel", "%d streams c=%d heavy step" % (S, OTW_C))
+    otw_roof = {"kernel": "otw_step_kernel", "bound": "hbm", "achieved": alg / (heavy_ms * 1e-3) / 1e9,
+                "peak": hbm_peak, "unit": "GB/s", "frac": alg / (heavy_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "measured" if "hbm_gbs" in peaks else "fallback", "algorithmic_bytes": alg, "traffic": tr, "kernel_ms": heavy_ms,
+                "traffic_source": tr_src,
                 "note": "the metric is latency; the step is a chain of <= 5 serial sweeps per stream on top of this traffic"}
     return {
         "metric": "otw_p99_frame_latency_ms", "value": o["p99_ms"], "unit": "ms", "n_gpus": world, "higher_is_better": False,

@@ -31,9 +31,9 @@ def _worker(rank, world, port, full_path, bounds, out_dir):
         k = int(np.nonzero((full_path == first).all(axis=1))[0][0])
         return seg, int(full_path[k - 1, 0])
 
-    seg = striped.handoff_backtrack(rank, world, local_backtrack, int(full_path[-1, 0]), dist)
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object(seg, gathered, dst=0)
+    group = dist.new_group(list(range(world)))           # an explicit group: ranks are passed through it everywhere
+    seg = striped.handoff_backtrack(rank, world, local_backtrack, int(full_path[-1, 0]), dist, group=group)
+    gathered = striped.gather_segments(seg, rank, world, dist, group=group)
     if rank == 0:
         np.save(os.path.join(out_dir, "path.npy"), striped.stitch_segments(gathered))
     dist.barrier()
