@@ -145,6 +145,15 @@ int afs_otw_path_layout(const afs_otw *h, int stream_idx, int64_t *offset, int64
 int afs_otw_path_ptr(const afs_otw *h, const int32_t **d_path, const int32_t **d_path_len);
 /* per-stream scalars (t, j) as the reference exposes .t/.j (.live_ptr/.ref_ptr) */
 int afs_otw_positions_ptr(const afs_otw *h, const int32_t **d_tj);
+/* On-demand view of the state the reference keeps in dense matrices (otw_eran.py:23-35: .acc_cost, .t, .j, .previous,
+ * .run_count, .direction; livenote_v2.py:22-38), for ONE stream, copied to the host (synchronises `stream`):
+ *   h_scalars[8] = t, j, previous, run_count, direction (0 "Both", 1 "Row", 2 "Column"; previous 0 = None), first_insert,
+ *                  status, path length
+ *   h_row[c + 1]  acc_cost[t, j - c + k]      h_col[c + 1]  acc_cost[t - c + k, j]        (k = 0 .. c)
+ *   h_live[12][c + 1]  the live frames t - c .. t (self.live[:, t - c + k])
+ * Indices before the start of the matrix read NaN; cells of the two lines the algorithm has not evaluated hold the
+ * reference's fill value (1e10 for OnlineTimeWarping, +inf for LiveNote).  Any output may be NULL. */
+int afs_otw_read_window(afs_otw *h, int stream_idx, int32_t *h_scalars, double *h_row, double *h_col, double *h_live, void *stream);
 
 /* ===================================================================== chroma
  * Replaces chroma.create_stft + create_chroma (chroma.py:44-75) == wtw.WTW.stft +
@@ -197,6 +206,14 @@ int afs_wtw_reset(afs_wtw *h, void *d_state, void *stream);
  * d_status (n_frames, n_streams): AFS_STEP_NONE / AFS_STEP_STOP (wtw.py:96-97). */
 int afs_wtw_push(afs_wtw *h, const double *d_cols, int n_frames, const uint8_t *d_active,
                  int32_t *d_status, void *stream);
+/* Audio in, alignment out: wtw.py:71-93 (WTW.insert) for a batch of streams without leaving the device.  Stream s
+ * contributes the samples d_audio[h_sample_off[s] .. h_sample_off[s+1]) (float32, offsets even), which must hold exactly
+ * n_frames un-padded frames (frame q = samples [q hop, q hop + 4096), wtw.py:81-83).  K1 computes their chroma columns
+ * (compute = AFS_F64 / AFS_F32 / AFS_BF16X3) into d_scratch (2 * n_frames * n_streams * 12 doubles, caller-provided),
+ * a small kernel reorders them and K6 consumes them, all on `stream`.  A stream that reports AFS_STEP_STOP for a frame
+ * does not consume the frames after it (the reference returns from insert() there; push them again). */
+int afs_wtw_push_audio(afs_wtw *h, afs_chroma_plan *plan, const float *d_audio, const int64_t *h_sample_off, int n_frames,
+                       double *d_scratch, const uint8_t *d_active, int32_t *d_status, int compute, void *stream);
 int afs_wtw_path_layout(const afs_wtw *h, int stream_idx, int64_t *offset, int64_t *capacity);
 int afs_wtw_path_ptr(const afs_wtw *h, const int32_t **d_path, const int32_t **d_path_len);
 /* per-stream (chroma_ptr, live_ptr, ref_ptr) */

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "afs_otw_path_layout": (C.c_int, [_vp, C.c_int, _i64p, _i64p]),
     "afs_otw_path_ptr": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "afs_otw_positions_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "afs_otw_read_window": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "afs_chroma_plan_create": (C.c_int, [C.POINTER(_vp), _vp, C.c_int, C.c_int, C.c_int]),
     "afs_chroma_plan_destroy": (C.c_int, [_vp]),
     "afs_chroma_num_frames": (C.c_int64, [_vp, C.c_int64, C.c_int]),
@@ -66,6 +67,7 @@ _SIGNATURES = {
     "afs_wtw_state_bytes": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),
     "afs_wtw_reset": (C.c_int, [_vp, _vp, _vp]),
     "afs_wtw_push": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "afs_wtw_push_audio": (C.c_int, [_vp, _vp, _vp, _i64p, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "afs_wtw_path_layout": (C.c_int, [_vp, C.c_int, _i64p, _i64p]),
     "afs_wtw_path_ptr": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "afs_wtw_positions_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),

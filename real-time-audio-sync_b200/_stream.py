@@ -11,8 +11,6 @@ except ImportError:
     import _native as nat
     from batch import OtwBatch
 
-_DIR_NAMES = {0: "Both", 1: "Row", 2: "Column"}
-
 
 class SingleStream(object):
     def __init__(self, kind, ref, band, max_run_count, chroma_diff=False):
@@ -52,6 +50,42 @@ class SingleStream(object):
 
     def _positions(self):
         return self._batch.positions()[0]
+
+    # --- the reference's state attributes, read from the device on demand (otw_eran.py:23-35, livenote_v2.py:22-38) ---
+    @property
+    def direction(self):
+        return self._batch.window(0)["direction"]
+
+    @property
+    def previous(self):
+        return self._batch.window(0)["previous"]
+
+    @property
+    def run_count(self):
+        return self._batch.window(0)["run_count"]
+
+    def acc_cost_window(self):
+        """The part of the reference's dense ``acc_cost`` the algorithm can still read: row t over columns j-c..j and
+        column j over rows t-c..t, as ``{(x, y): value}`` (never-evaluated cells hold the reference's fill value)."""
+        w = self._batch.window(0)
+        out = {(w["t"], int(y)): float(v) for y, v in zip(w["cols"], w["acc_row"])}
+        out.update({(int(x), w["j"]): float(v) for x, v in zip(w["rows"], w["acc_col"])})
+        return out
+
+    def cost_window(self):
+        """Local costs of the same cells (the reference's dense ``cost``), recomputed from the live frames the device
+        keeps: 1 - <live, ref> for chroma (otw_eran.py:216, livenote_v2.py:170), Euclidean distance for chroma_diff."""
+        w = self._batch.window(0)
+        ref = np.asarray(self._ref, dtype=np.float64)
+        euclid = getattr(self._batch, "chroma_diff", False)
+
+        def cost(lv, rf):
+            return float(np.sqrt(np.sum((lv - rf) ** 2))) if euclid else float(1 - np.dot(lv, rf))
+
+        cur = w["live"][:, -1]
+        out = {(w["t"], int(y)): cost(cur, ref[:, int(y)]) for y in w["cols"]}
+        out.update({(int(x), w["j"]): cost(w["live"][:, k], ref[:, w["j"]]) for k, x in enumerate(w["rows"])})
+        return out
 
     def close(self):
         self._batch.close()

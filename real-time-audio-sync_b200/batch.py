@@ -42,6 +42,7 @@ class OtwBatch(object):
         self.device = nat.device() if device is None else torch.device(device)
         self.kind = {"otw": nat.AFS_OTW, "livenote_v2": nat.AFS_LIVENOTE_V2, "livenote": nat.AFS_LIVENOTE_V1}[kind]
         self.c = int(c)
+        self.chroma_diff = bool(chroma_diff)
         self.max_run_count = int(max_run_count)
         with torch.cuda.device(self.device):
             self.d_ref, self.ref_lens, self.ref_offs = _pack_refs(refs, self.device)
@@ -158,6 +159,28 @@ class OtwBatch(object):
         nat.check(nat.lib().afs_otw_positions_ptr(self._h, C.byref(p)))
         return self._dev_view(p.value, 2 * self.n, torch.int32).cpu().numpy().reshape(self.n, 2)
 
+    def window(self, stream=0):
+        """On-demand view of one stream's state in the reference's terms (otw_eran.py:23-35, livenote_v2.py:22-38):
+        dict with the scalars t, j, previous, run_count, direction (as the reference's strings) and the two live lines
+        of acc_cost — ``acc_row`` = acc_cost[t, j-c .. j], ``acc_col`` = acc_cost[t-c .. t, j] — with the column / row
+        indices they belong to, plus the last c+1 live frames.  Indices before the matrix start are dropped."""
+        c = int(self.c)
+        scal = np.zeros(8, dtype=np.int32)
+        row = np.empty(c + 1, dtype=np.float64)
+        col = np.empty(c + 1, dtype=np.float64)
+        live = np.empty((12, c + 1), dtype=np.float64)
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().afs_otw_read_window(self._h, int(stream), scal.ctypes.data_as(C.c_void_p), row.ctypes.data_as(C.c_void_p),
+                                                    col.ctypes.data_as(C.c_void_p), live.ctypes.data_as(C.c_void_p), nat.stream_ptr()))
+        t, j = int(scal[0]), int(scal[1])
+        names = {0: "Both", 1: "Row", 2: "Column"}
+        cols = np.arange(j - c, j + 1)
+        rows = np.arange(t - c, t + 1)
+        return {"t": t, "j": j, "previous": None if scal[2] == 0 else names[int(scal[2])], "run_count": int(scal[3]),
+                "direction": names[int(scal[4])], "first_insert": bool(scal[5]), "status": int(scal[6]), "path_len": int(scal[7]),
+                "cols": cols[cols >= 0], "acc_row": row[cols >= 0], "rows": rows[rows >= 0], "acc_col": col[rows >= 0],
+                "live": live[:, rows >= 0]}
+
     def paths(self):
         """Full device-resident paths as a list of int64 (P,2) arrays."""
         pp, pl = C.c_void_p(), C.c_void_p()
@@ -224,6 +247,22 @@ class WtwBatch(object):
         nf = int(d_cols.shape[0])
         st = torch.empty((nf, self.n), dtype=torch.int32, device=self.device)
         nat.check(nat.lib().afs_wtw_push(self._h, nat.ptr(d_cols), nf, nat.ptr(active), nat.ptr(st), nat.stream_ptr()))
+        return st
+
+    def push_audio_device(self, plan, d_audio, offsets, n_frames, compute="fp64", active=None):
+        """Audio in, alignment out on the device (afs_wtw_push_audio: K1 -> reorder -> K6 on the current stream).
+        d_audio: float32 device tensor holding one run of samples per stream, offsets (n + 1) int64 (even), every run
+        exactly n_frames un-padded frames (wtw.py:81-83).  Returns the device status tensor (n_frames, n)."""
+        assert d_audio.is_cuda and d_audio.dtype == torch.float32
+        offs = np.ascontiguousarray(offsets, dtype=np.int64)
+        assert offs.shape[0] == self.n + 1
+        nf = int(n_frames)
+        st = torch.empty((nf, self.n), dtype=torch.int32, device=self.device)
+        scratch = torch.empty(2 * nf * self.n * 12, dtype=torch.float64, device=self.device)
+        code = {"fp64": nat.AFS_F64, "f64": nat.AFS_F64, "fp32": nat.AFS_F32, "f32": nat.AFS_F32, "tc": nat.AFS_BF16X3}[compute]
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().afs_wtw_push_audio(self._h, plan._h, nat.ptr(d_audio), offs.ctypes.data_as(nat._i64p), nf, nat.ptr(scratch),
+                                                   nat.ptr(active), nat.ptr(st), code, nat.stream_ptr()))
         return st
 
     def push(self, cols):

@@ -25,6 +25,7 @@
 // per lane), then every warp writes its line back.
 #include <math_constants.h>
 
+#include <limits>
 #include <vector>
 
 #include "afs_common.cuh"
@@ -625,6 +626,35 @@ int afs_otw_positions_ptr(const afs_otw *h, const int32_t **d_tj)
 {
     if (!h || !h->bound || !d_tj) return afs::fail(AFS_ERR_INVALID, "afs_otw_positions_ptr: state not bound");
     *d_tj = h->args.tj;
+    return AFS_OK;
+}
+
+int afs_otw_read_window(afs_otw *h, int stream_idx, int32_t *h_scalars, double *h_row, double *h_col, double *h_live, void *stream)
+{
+    if (!h || !h->bound) return afs::fail(AFS_ERR_INVALID, "afs_otw_read_window: state not bound");
+    if (stream_idx < 0 || stream_idx >= h->args.n_streams) return afs::fail(AFS_ERR_INVALID, "afs_otw_read_window: bad stream");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const OtwArgs &a = h->args;
+    const int rs = a.rs, c = a.c;
+    OtwScalars S;
+    std::vector<double> rw(rs), cl(rs), lh((size_t)rs * kF);
+    AFS_CUDA(cudaMemcpyAsync(&S, a.scal + stream_idx, sizeof(S), cudaMemcpyDeviceToHost, st));
+    AFS_CUDA(cudaMemcpyAsync(rw.data(), a.rw + (int64_t)stream_idx * rs, sizeof(double) * rs, cudaMemcpyDeviceToHost, st));
+    AFS_CUDA(cudaMemcpyAsync(cl.data(), a.cl + (int64_t)stream_idx * rs, sizeof(double) * rs, cudaMemcpyDeviceToHost, st));
+    AFS_CUDA(cudaMemcpyAsync(lh.data(), a.lh + (int64_t)stream_idx * rs * kF, sizeof(double) * rs * kF, cudaMemcpyDeviceToHost, st));
+    AFS_CUDA(cudaStreamSynchronize(st));
+    if (h_scalars) {
+        h_scalars[0] = S.t; h_scalars[1] = S.j; h_scalars[2] = S.previous; h_scalars[3] = S.run_count; h_scalars[4] = S.direction;
+        h_scalars[5] = S.first; h_scalars[6] = S.status; h_scalars[7] = S.path_len;
+    }
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (int k = 0; k <= c; k++) {
+        const int col = S.j - c + k, row = S.t - c + k;      // slot = index mod (c + 1)
+        if (h_row) h_row[k] = col >= 0 ? rw[col % rs] : nan;
+        if (h_col) h_col[k] = row >= 0 ? cl[row % rs] : nan;
+        if (h_live)
+            for (int f = 0; f < kF; f++) h_live[(size_t)f * (c + 1) + k] = row >= 0 ? lh[(size_t)f * rs + row % rs] : nan;
+    }
     return AFS_OK;
 }
 

@@ -67,6 +67,18 @@ __device__ __forceinline__ double norm12(const double *x)
     return __dsqrt_rn(s);
 }
 
+// K1's output (stream, feature, frame) -> K6's input (frame, stream, feature)
+__global__ void wtw_transpose_cols(const double *__restrict__ src, double *__restrict__ dst, int n_streams, int n_frames)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)n_streams * n_frames * kF;
+    if (i >= total) return;
+    const int k = (int)(i % kF);
+    const int64_t fs = i / kF;
+    const int s = (int)(fs % n_streams), f = (int)(fs / n_streams);
+    dst[i] = src[((int64_t)s * kF + k) * n_frames + f];
+}
+
 __global__ void __launch_bounds__(kWtwThreads) wtw_push_kernel(const WtwArgs a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -90,13 +102,18 @@ __global__ void __launch_bounds__(kWtwThreads) wtw_push_kernel(const WtwArgs a)
     if (t == 0) S = a.scal[s];
     __syncthreads();
 
+    // wtw.py:96-97 returns from insert() at the first stopping frame and leaves the rest of the buffer unread: the frames
+    // that follow a STOP inside this launch are not consumed (the caller pushes them again, as the reference re-reads them)
+    bool stopped_in_launch = false;          // thread 0 only
     for (int f = 0; f < a.n_frames; f++) {
         const int64_t oidx = (int64_t)f * a.n_streams + s;
         const bool on = (a.active == nullptr) || (a.active[s] != 0);
         if (t == 0) {
             int status = AFS_STEP_NONE;
             s_do_window = 0;
-            if (on) {
+            if (on && stopped_in_launch) {
+                status = AFS_STEP_STOP;
+            } else if (on) {
                 if (S.chroma_ptr >= Ncap) {
                     status = AFS_STEP_FULL;            // the reference would raise IndexError at wtw.py:92
                 } else {
@@ -105,7 +122,7 @@ __global__ void __launch_bounds__(kWtwThreads) wtw_push_kernel(const WtwArgs a)
                     double *dst = ring + (int64_t)(S.chroma_ptr % W) * kF;
                     for (int k = 0; k < kF; k++) dst[k] = col[k];
                     S.chroma_ptr += 1;
-                    if (S.ref_ptr >= (M - 1 - W) || S.live_ptr >= (Ncap - 1 - W)) status = AFS_STEP_STOP;   // wtw.py:96-97
+                    if (S.ref_ptr >= (M - 1 - W) || S.live_ptr >= (Ncap - 1 - W)) { status = AFS_STEP_STOP; stopped_in_launch = true; }   // wtw.py:96-97
                     else if (S.chroma_ptr - S.live_ptr >= W) s_do_window = 1;                             // wtw.py:100
                 }
             }
@@ -326,6 +343,32 @@ int afs_wtw_push(afs_wtw *h, const double *d_cols, int n_frames, const uint8_t *
     afs::count_launch();
     AFS_CUDA(cudaGetLastError());
     return AFS_OK;
+}
+
+int afs_wtw_push_audio(afs_wtw *h, afs_chroma_plan *plan, const float *d_audio, const int64_t *h_sample_off, int n_frames,
+                       double *d_scratch, const uint8_t *d_active, int32_t *d_status, int compute, void *stream)
+{
+    if (!h || !plan || !d_audio || !h_sample_off || !d_scratch || n_frames <= 0)
+        return afs::fail(AFS_ERR_INVALID, "afs_wtw_push_audio: null argument or n_frames <= 0");
+    if (!h->bound) return afs::fail(AFS_ERR_INVALID, "afs_wtw_push_audio: call afs_wtw_reset first");
+    const int n = h->args.n_streams;
+    std::vector<int64_t> out_off(n);
+    for (int s = 0; s < n; s++) {
+        const int64_t got = afs_chroma_num_frames(plan, h_sample_off[s + 1] - h_sample_off[s], 0);
+        if (got != n_frames)
+            return afs::fail(AFS_ERR_INVALID, "afs_wtw_push_audio: stream %d holds %lld frames, expected %d", s, (long long)got, n_frames);
+        out_off[s] = (int64_t)s * n_frames;
+    }
+    // K1: frames without padding (wtw.py:81-90), float64 columns, track-major (12, n_frames) per stream
+    double *d_chroma = d_scratch, *d_cols = d_scratch + (size_t)n * n_frames * kF;
+    const int rc = afs_chroma_batch(plan, d_audio, h_sample_off, n, 0, 1, d_chroma, out_off.data(), AFS_F64, compute, stream);
+    if (rc != AFS_OK) return rc;
+    // (stream, feature, frame) -> (frame, stream, feature), the order K6 reads
+    const int64_t total = (int64_t)n * n_frames * kF;
+    wtw_transpose_cols<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_chroma, d_cols, n, n_frames);
+    afs::count_launch();
+    AFS_CUDA(cudaGetLastError());
+    return afs_wtw_push(h, d_cols, n_frames, d_active, d_status, stream);
 }
 
 int afs_wtw_path_layout(const afs_wtw *h, int stream_idx, int64_t *offset, int64_t *capacity)

@@ -75,9 +75,13 @@ class WTW():
         # every complete frame of this call: frame q = buf[q*hop : q*hop + fft_len]  (wtw.py:81-83)
         n_frames = (len(self.buf) - self.fft_len) // self.hop_size + 1
         used = (n_frames - 1) * self.hop_size + self.fft_len
-        cols = self._chroma_of(self.buf[:used], center=False)         # (12, n_frames), wtw.py:84-90
-        d_cols = torch.from_numpy(np.ascontiguousarray(cols.T).reshape(n_frames, 1, 12)).to(self._batch.device)
-        status = self._batch.push_device(d_cols).cpu().numpy()[:, 0]
+        # chroma of every frame (wtw.py:84-90) and the windowed DTW steps they trigger, chained on the device
+        x = np.zeros(used + (used & 1), dtype=np.float32)
+        x[:used] = self.buf[:used]
+        d_audio = torch.from_numpy(x).to(self._batch.device)
+        status = self._batch.push_audio_device(self._plan, d_audio, [0, used], n_frames, compute=self._compute).cpu().numpy()[:, 0]
+        if (status == nat.AFS_STEP_FULL).any():
+            raise IndexError("WTW.insert: the live chroma buffer (2 x reference frames) is full (wtw.py:92 raises here too)")
         stops = np.nonzero(status == nat.AFS_STEP_STOP)[0]
         self._pos = tuple(int(v) for v in self._batch.positions()[0])
         if len(stops):

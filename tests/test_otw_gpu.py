@@ -241,3 +241,44 @@ def test_full_config_4096_streams_c500_sampled_parity(mods, orc, kind):
         assert np.array_equal(got[s], o.path_array()), (kind, s)
         assert (int(pos[s, 0]), int(pos[s, 1])) == (o.t, o.j), (kind, s)
     b.close()
+
+
+@pytest.mark.parametrize("kind", ["otw", "livenote_v2", "livenote_v2_diff"])
+def test_on_demand_state_views_match_the_dense_matrices(mods, orc, kind):
+    """The reference's .acc_cost / .cost / .direction / .previous / .run_count (otw_eran.py:23-35, livenote_v2.py:22-38)
+    are read back on demand from the device's moving window: every cell of row t over columns j-c..j and of column j over
+    rows t-c..t must equal the oracle's dense acc_cost bit for bit, at every step of a run."""
+    rng = np.random.default_rng(11)
+    ref = chroma_like(rng, 140)
+    live = warped_copy(rng, ref, 170)
+    c, mr = 12, 3
+    diff = kind == "livenote_v2_diff"
+    if kind == "otw":
+        obj = mods["otw_eran"].OnlineTimeWarping(ref, {"c": c, "max_run_count": mr})
+        ora = orc.OnlineTimeWarping(ref, {"c": c, "max_run_count": mr})
+    else:
+        p = {"search_band_width": c, "max_run_count": mr}
+        obj = mods["livenote_v2"].LiveNoteV2(ref, p, chroma_diff=diff)
+        ora = orc.LiveNoteV2(ref, p, chroma_diff=diff)
+    checked = 0
+    for i in range(live.shape[1]):
+        r1, r2 = obj.insert(live[:, i]), ora.insert(live[:, i])
+        assert r1 == r2
+        if r1 == "stop":
+            break
+        if i % 7 and i > 3:
+            continue
+        w = obj._batch.window(0)
+        assert (w["t"], w["j"]) == (ora.t, ora.j)
+        assert w["direction"] in ("Both", "Row", "Column") and w["previous"] in (None, "Row", "Column") and w["run_count"] >= 0
+        for (x, y), v in obj.acc_cost_window().items():
+            want = ora.acc(x, y)
+            assert v == want or (np.isinf(v) and np.isinf(want)), (i, x, y, v, want)
+            checked += 1
+        cw = obj.cost_window()
+        lv = live[:, ora.t]
+        for y in w["cols"]:
+            want = float(np.sqrt(np.sum((lv - ref[:, y]) ** 2))) if diff else float(1 - np.dot(lv, ref[:, y]))
+            assert abs(cw[(w["t"], int(y))] - want) < 1e-12
+    assert checked > 300
+    assert obj.direction in ("Both", "Row", "Column")
