@@ -42,6 +42,7 @@ struct WtwArgs {
     int n_frames;
     const uint8_t *active;
     int32_t *out_status;
+    int latch_stop;       // 1: frames that follow a STOP inside this launch are not consumed (one insert() call of many frames)
 };
 
 // np.dot on two strided column views: OpenBLAS generic ddot
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(kWtwThreads) wtw_push_kernel(const WtwArgs a)
         if (t == 0) {
             int status = AFS_STEP_NONE;
             s_do_window = 0;
-            if (on && stopped_in_launch) {
+            if (on && stopped_in_launch && a.latch_stop) {
                 status = AFS_STEP_STOP;
             } else if (on) {
                 if (S.chroma_ptr >= Ncap) {
@@ -330,7 +331,8 @@ int afs_wtw_reset(afs_wtw *h, void *d_state, void *stream)
     return AFS_OK;
 }
 
-int afs_wtw_push(afs_wtw *h, const double *d_cols, int n_frames, const uint8_t *d_active, int32_t *d_status, void *stream)
+static int wtw_push_impl(afs_wtw *h, const double *d_cols, int n_frames, const uint8_t *d_active, int32_t *d_status, int latch_stop,
+                         void *stream)
 {
     if (!h || !d_cols || n_frames <= 0) return afs::fail(AFS_ERR_INVALID, "afs_wtw_push: null argument or n_frames <= 0");
     if (!h->bound) return afs::fail(AFS_ERR_INVALID, "afs_wtw_push: call afs_wtw_reset first");
@@ -339,10 +341,17 @@ int afs_wtw_push(afs_wtw *h, const double *d_cols, int n_frames, const uint8_t *
     a.n_frames = n_frames;
     a.active = d_active;
     a.out_status = d_status;
+    a.latch_stop = latch_stop;
     wtw_push_kernel<<<a.n_streams, kWtwThreads, h->smem_bytes, static_cast<cudaStream_t>(stream)>>>(a);
     afs::count_launch();
     AFS_CUDA(cudaGetLastError());
     return AFS_OK;
+}
+
+int afs_wtw_push(afs_wtw *h, const double *d_cols, int n_frames, const uint8_t *d_active, int32_t *d_status, void *stream)
+{
+    // every column is an insert of its own (a STOP does not swallow the columns after it)
+    return wtw_push_impl(h, d_cols, n_frames, d_active, d_status, 0, stream);
 }
 
 int afs_wtw_push_audio(afs_wtw *h, afs_chroma_plan *plan, const float *d_audio, const int64_t *h_sample_off, int n_frames,
@@ -368,7 +377,7 @@ int afs_wtw_push_audio(afs_wtw *h, afs_chroma_plan *plan, const float *d_audio, 
     wtw_transpose_cols<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_chroma, d_cols, n, n_frames);
     afs::count_launch();
     AFS_CUDA(cudaGetLastError());
-    return afs_wtw_push(h, d_cols, n_frames, d_active, d_status, stream);
+    return wtw_push_impl(h, d_cols, n_frames, d_active, d_status, 1, stream);
 }
 
 int afs_wtw_path_layout(const afs_wtw *h, int stream_idx, int64_t *offset, int64_t *capacity)

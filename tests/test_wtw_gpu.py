@@ -76,9 +76,10 @@ def test_audio_in_path_out_matches_oracle(mods, orc):
             break
     assert w.path == o.path and len(w.path) > 100
     assert (w.live_ptr, w.ref_ptr) == (o.live_ptr, o.ref_ptr)
-    # a finished aligner fed several frames per call keeps answering "stop" and stays in step with the reference
-    # (the kernel must not consume the frames that follow a stop inside one launch)
-    for _ in range(3):
-        big = mono["live"][:9000].tolist()
-        assert w.insert(big) == o.insert(big) == "stop"
-    assert (w.live_ptr, w.ref_ptr) == (o.live_ptr, o.ref_ptr)
+    # an aligner that has reported "stop", fed several frames per call, stays in step with the reference (the kernel must not
+    # consume the frames that follow a stop inside one launch: the reference returns there and re-reads them next time)
+    for k in range(4):
+        big = mono["live"][k * 3000 : k * 3000 + 9000].tolist()
+        assert w.insert(big) == o.insert(big), k
+        assert (w.live_ptr, w.ref_ptr) == (o.live_ptr, o.ref_ptr)
+    assert w.path == o.path
