@@ -117,8 +117,9 @@ class OtwBatch(object):
         assert d_frames.shape[1] == self.n and d_frames.shape[2] == 12
         nf = int(d_frames.shape[0])
         st, npts, pts = self._outputs(nf)
-        nat.check(nat.lib().afs_otw_step(self._h, nat.ptr(d_frames), nf, nat.ptr(active), nat.ptr(st), nat.ptr(npts),
-                                         nat.ptr(pts) if want_points else C.c_void_p(0), nat.stream_ptr()))
+        with torch.cuda.device(self.device):      # the launch goes to the batch's GPU whatever the caller's current device is
+            nat.check(nat.lib().afs_otw_step(self._h, nat.ptr(d_frames), nf, nat.ptr(active), nat.ptr(st), nat.ptr(npts),
+                                             nat.ptr(pts) if want_points else C.c_void_p(0), nat.stream_ptr()))
         return st, npts, pts
 
     def insert(self, frames):
@@ -246,7 +247,8 @@ class WtwBatch(object):
         assert d_cols.shape[1] == self.n and d_cols.shape[2] == 12
         nf = int(d_cols.shape[0])
         st = torch.empty((nf, self.n), dtype=torch.int32, device=self.device)
-        nat.check(nat.lib().afs_wtw_push(self._h, nat.ptr(d_cols), nf, nat.ptr(active), nat.ptr(st), nat.stream_ptr()))
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().afs_wtw_push(self._h, nat.ptr(d_cols), nf, nat.ptr(active), nat.ptr(st), nat.stream_ptr()))
         return st
 
     def push_audio_device(self, plan, d_audio, offsets, n_frames, compute="fp64", active=None):

@@ -22,15 +22,16 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count()
 {
-    static int cached = 0;
-    if (!cached) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    // per device: a process may drive several GPUs (the plans carry their device)
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
         int n = 0;
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-        cached = n;
+        cached[dev] = n;
     }
-    return cached;
+    return cached[dev];
 }
 
 }  // namespace afs

@@ -83,14 +83,16 @@ class DtwPlan(object):
         (12, len) block at the plan's offsets, in the plan dtype."""
         assert d_a.dtype == self.torch_dtype and d_b.dtype == self.torch_dtype
         assert d_a.is_cuda and d_b.is_cuda
-        nat.check(nat.lib().afs_dtw_accumulate(self._h, nat.ptr(d_a), nat.ptr(d_b), nat.ptr(self.workspace),
-                                                nat.ptr(self.acc_end), nat.ptr(dense_cost), nat.ptr(dense_acc),
-                                                nat.stream_ptr()))
+        with torch.cuda.device(self.device):      # the launch goes to the plan's GPU whatever the caller's current device is
+            nat.check(nat.lib().afs_dtw_accumulate(self._h, nat.ptr(d_a), nat.ptr(d_b), nat.ptr(self.workspace),
+                                                    nat.ptr(self.acc_end), nat.ptr(dense_cost), nat.ptr(dense_acc),
+                                                    nat.stream_ptr()))
 
     def backtrack(self):
         """K3 on the current stream."""
-        nat.check(nat.lib().afs_dtw_backtrack(self._h, nat.ptr(self.workspace), nat.ptr(self.path),
-                                               nat.ptr(self.path_start), nat.ptr(self.path_len), nat.stream_ptr()))
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().afs_dtw_backtrack(self._h, nat.ptr(self.workspace), nat.ptr(self.path),
+                                                   nat.ptr(self.path_start), nat.ptr(self.path_len), nat.stream_ptr()))
 
     def run(self, d_a, d_b):
         self.accumulate(d_a, d_b)

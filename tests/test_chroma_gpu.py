@@ -176,3 +176,19 @@ def test_full_config_1024_tracks_sampled_parity(chroma, orc):
         got = cols[k].cpu().numpy().astype(np.float64)
         assert got.shape == want.shape
         assert np.abs(got - want).max() < TOL_F32, k
+
+
+def test_create_stft_is_the_reference_spectrum(chroma, audio, orc):
+    """chroma.create_stft (chroma.py:44-65) returns the complex (2049, M) spectrum itself (float64 kernel, materialised by
+    afs_stft_batch): equal to numpy's rfft of the windowed, left-padded frames to 1e-9 of the spectrum's peak; and
+    create_chroma of an arbitrary spectrum array (not produced by create_stft) goes through filterbank + normalisation."""
+    x = audio["ref"][: 22050 * 4]
+    got = chroma.create_stft(x)
+    want = orc.create_stft(x)
+    assert got.shape == want.shape and got.shape[0] == 2049 and np.iscomplexobj(got)
+    assert np.abs(np.asarray(got) - want).max() <= 1e-9 * np.abs(want).max()
+    c1 = chroma.create_chroma(np.array(want))            # a plain ndarray: the spectrum path
+    c2 = orc.create_chroma(want)
+    assert np.abs(c1 - c2).max() < 1e-9
+    c3 = chroma.create_chroma(got)                      # the object create_stft returned: fused path from the samples
+    assert np.abs(c3 - c2).max() < 1e-4
