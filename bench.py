@@ -33,6 +33,37 @@ FP64_LANES_PER_SM = 64          # B200 FP64 FMA lanes per SM
 DTW_FLOP_PER_CELL = 31          # 12 FMA + sub + scale + 3 add + 2 cmp/sel
 
 
+def bind_to_gpu_numa(torch, local, world):
+    """Pin this rank to cores of the NUMA node its GPU hangs off, before any pinned host buffer is allocated (first touch
+    then places the buffers on that node): with every rank on node 0, the ranks of the far GPUs stage their uploads through
+    the inter-socket link.  Returns what was done, for the JSON line."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        props = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = []
+            for part in fh.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return info
+        # ranks whose GPUs share the node take disjoint slices of its cores
+        per_node = max(1, world // max(1, len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])))
+        k = local % per_node
+        share = allowed[k * len(allowed) // per_node:(k + 1) * len(allowed) // per_node] or allowed
+        os.sched_setaffinity(0, share)
+        info = {"numa_node": node, "cpus": "%d-%d (%d cores)" % (share[0], share[-1], len(share))}
+    except Exception as exc:
+        info["error"] = repr(exc)[:120]
+    return info
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -211,6 +242,7 @@ def main():
     world = env_int("WORLD_SIZE", 1)
     local = env_int("LOCAL_RANK", 0)
     torch.cuda.set_device(local)
+    affinity = bind_to_gpu_numa(torch, local, world) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -260,6 +292,7 @@ def main():
             if k != head_key:
                 line[k] = v
         line["clocks"] = clocks
+        line["host_affinity_rank0"] = affinity
         # the figures of the other workloads once more as flat scalars, so that they survive any post-processing that keeps
         # only the top level of the line
         def pick(key, *path):

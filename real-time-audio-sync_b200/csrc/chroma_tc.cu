@@ -81,7 +81,7 @@ constexpr uint32_t kSmemA = kOffRing + kRingSlots * kSlotBytes;          // 229 
 constexpr uint32_t kColGhi = 0, kColGlo = 64, kColA1 = 128, kColD1 = 192, kColD2 = 320;
 // mbarriers
 enum { kBarA1Full = 0, kBarM1Done = 1, kBarD1Free = 3, kBarYFull = 5, kBarM2Done = 7, kBarD2Free = 9, kBarStored = 10, kBarSlotOk = 11,
-       kBarRingFull = 12, kBarRingEmpty = 12 + kRingSlots, kNumBars = 12 + 2 * kRingSlots };
+       kBarRingFull = 13, kBarRingEmpty = 13 + kRingSlots, kNumBars = 13 + 2 * kRingSlots };
 
 // what the loader tells the converters about a ring slot
 struct SlotInfo {
@@ -436,6 +436,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
         afs::mbar_init(&s_bar[kBarD2Free], kWarpsE2);
         afs::mbar_init(&s_bar[kBarStored], kWarpsE2);
         afs::mbar_init(&s_bar[kBarSlotOk], 1);
+        afs::mbar_init(&s_bar[kBarSlotOk + 1], 1);
         for (int r = 0; r < kRingSlots; r++) {
             afs::mbar_init(&s_bar[kBarRingFull + r], 1);
             afs::mbar_init(&s_bar[kBarRingEmpty + r], kWarpsC);
@@ -666,7 +667,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
                 if (odd) own[16] = 0.f;
                 own[17] = 0.f;
                 const int64_t fl = 4 * g + fq;                           // frame of the launch
-                if (q == 0) mbar_wait_sleep(&s_bar[kBarSlotOk], (uint32_t)(gi & 1));     // the ring slot is free (publisher warp)
+                if (q == 0) mbar_wait_sleep(&s_bar[kBarSlotOk + (gi & 1)], (uint32_t)((gi >> 1) & 1));     // the ring slot is free (publisher warp)
                 if (fl < n_frames) {
                     // A-operand image of the filterbank tile: word i * 128 + ln of the frame's plane -> K block 4 i + ln / 32,
                     // row 2 r + plane, 16-byte chunk ((ln % 32) / 4) ^ (row & 7)
@@ -703,11 +704,14 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
             if (lane == 0) {
                 // the slot's previous tile must have been consumed by its filterbank CTA
                 while (afs::ld_acquire(args.cons + slot) < use) __nanosleep(100);
-                mbar_arrive(&s_bar[kBarSlotOk]);
+                mbar_arrive(&s_bar[kBarSlotOk + (gi & 1)]);
             }
             __syncwarp();
         };
+        // the slot checks run two groups ahead of the epilogue (two barriers, alternating), so their L2 round trip is never
+        // on the epilogue's path
         wait_slot_free(0);
+        if (n_local > 1) wait_slot_free(1);
         for (int gi = 0; gi < n_local; gi++) {
             int slot, use;
             slot_of(gi, slot, use);
@@ -720,7 +724,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
             }
             __syncwarp();
             trace(1, gi);
-            if (gi + 1 < n_local) wait_slot_free(gi + 1);
+            if (gi + 2 < n_local) wait_slot_free(gi + 2);
             trace(2, gi);
         }
     } else if (warp > kWarpsC + kWarpsE1 + kWarpsE2) {

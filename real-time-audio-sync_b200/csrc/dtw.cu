@@ -204,7 +204,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     } while (!done);
 }
 
-// hand-off records are read/written with single 128-bit volatile accesses (never cached in L1)
+// Hand-off records are read/written with single 128-bit volatile accesses (never cached in L1).
+// What the protocol relies on, and what it does not.  A record is {value lo, tag, value hi, tag}: each 64-bit half carries
+// its own copy of the (launch epoch, band) tag, and a reader accepts a record only when BOTH tags match, so the protocol
+// needs single-copy atomicity of aligned 64-bit halves only (which PTX guarantees for naturally aligned accesses of up to
+// 64 bits), not of the whole 16-byte vector: a torn 128-bit access shows one stale half, whose tag is the previous band's or
+// launch's and fails the comparison; the reader polls again.  What PTX does not promise is that the two halves of ONE
+// st.v4 become visible in program order to a concurrent ld.v4 — irrelevant here because either order is detected.  The
+// payload needs no fence: it IS the flagged word.  tests/test_dtw_gpu.py::test_band_handoff_stress_under_memory_pressure
+// hammers the path (240 launches, alternating inputs on one workspace, memory hog on a second stream) in lieu of racecheck.
 __device__ __forceinline__ uint4 ld_record(const uint4 *p)
 {
     uint4 v;
