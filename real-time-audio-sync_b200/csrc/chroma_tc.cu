@@ -129,17 +129,35 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
 }
 
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-// mbarrier wait with a long suspend-time hint: the warp sleeps in hardware until the phase completes instead of
-// re-issuing try_wait every few hundred cycles (a third of all issued instructions in the first profile were such spins)
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
+// mbarrier wait that backs off with nanosleep between probes, for the roles that idle most of the time (epilogues,
+// loaders, publisher).  A bare try_wait loop re-issues every few hundred cycles (the suspend-time hint does not change
+// that on this part): those probes were 53 % of all instructions the kernel executed (profiles/ncu_lines_r2_chroma_tc.txt).
+// Measured effect on throughput: none either way (169 vs 166 Mframes/s: the probes only take issue slots nobody else
+// wanted), while sleeping on the converter <-> issuer chain costs 15 % (wake-up latency) — so those two spin.
+#ifndef AFS_TC_WAIT_NS
+#define AFS_TC_WAIT_NS 200
+#endif
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity)
 {
     uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(afs::smem_addr(bar)), "r"(parity)
+                 : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
+{
+    if (mbar_try(bar, parity)) return;
     do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done)
-                     : "r"(afs::smem_addr(bar)), "r"(parity), "r"(20000u)
-                     : "memory");
-    } while (!done);
+        __nanosleep(AFS_TC_WAIT_NS);
+    } while (!mbar_try(bar, parity));
+}
+// the waits on the critical chain (converter <-> MMA issuer) keep probing
+__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try(bar, parity)) {
+    }
 }
 // keep the computation of v before whatever volatile operation follows (the scheduler otherwise sinks it behind the wait)
 __device__ __forceinline__ void pin16(uint32_t (&v)[16])
@@ -499,7 +517,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
             float x[32];
 #pragma unroll
             for (int half = 0; half < 2; half++) {
-                mbar_wait_sleep(&s_bar[kBarRingFull + stage], ring_phase);
+                mbar_wait_spin(&s_bar[kBarRingFull + stage], ring_phase);
                 if (straddle_warp && !s_slot[stage].shared) {
                     // the tile straddles two tracks (or ends the chunk): guarded loads from global memory instead
                     const SlotInfo si = s_slot[stage];
@@ -535,7 +553,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
             pin16(l);
             trace(1, T);
             // A1 is single-buffered: the MMAs of the previous tile must have read it
-            if (T > 0) mbar_wait_sleep(&s_bar[kBarM1Done + ((T - 1) & 1)], (uint32_t)(((T - 1) >> 1) & 1));
+            if (T > 0) mbar_wait_spin(&s_bar[kBarM1Done + ((T - 1) & 1)], (uint32_t)(((T - 1) >> 1) & 1));
             trace(2, T);
             tc::tmem_st16(a1_col, h);
             tc::tmem_st16(a1_col + 32, l);
@@ -790,8 +808,8 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
         constexpr uint32_t idesc1 = tc::idesc_bf16_f32(128, kN1), idesc2 = tc::idesc_bf16_f32(128, kN2);
         auto stage1 = [&](int T) {
             const int s = T & 1, use = T >> 1;
-            mbar_wait_sleep(&s_bar[kBarA1Full], (uint32_t)(T & 1));
-            if (use > 0) mbar_wait_sleep(&s_bar[kBarD1Free + s], (uint32_t)((use - 1) & 1));
+            mbar_wait_spin(&s_bar[kBarA1Full], (uint32_t)(T & 1));
+            if (use > 0) mbar_wait_spin(&s_bar[kBarD1Free + s], (uint32_t)((use - 1) & 1));
             tc::fence_after_sync();
             trace(0, T);
             const uint32_t d1 = tm + kColD1 + 64 * s, a_hi = tm + kColA1, a_lo = a_hi + 32;
@@ -806,8 +824,8 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
         };
         auto stage2 = [&](int gi) {
             const int b = gi & 1, u = gi >> 1;
-            mbar_wait_sleep(&s_bar[kBarYFull + b], (uint32_t)(u & 1));
-            if (gi > 0) mbar_wait_sleep(&s_bar[kBarD2Free], (uint32_t)((gi - 1) & 1));
+            mbar_wait_spin(&s_bar[kBarYFull + b], (uint32_t)(u & 1));
+            if (gi > 0) mbar_wait_spin(&s_bar[kBarD2Free], (uint32_t)((gi - 1) & 1));
             tc::fence_after_sync();
             trace(2, gi);
             const uint64_t y_hi_desc = tc::smem_desc_k_sw128(s_base + kOffY + (uint32_t)b * kYBuf);
@@ -831,7 +849,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
         }
         stage2(n_local - 1);
         // drain: the last commit covers every MMA issued before it
-        mbar_wait_sleep(&s_bar[kBarM2Done + ((n_local - 1) & 1)], (uint32_t)(((n_local - 1) >> 1) & 1));
+        mbar_wait_spin(&s_bar[kBarM2Done + ((n_local - 1) & 1)], (uint32_t)(((n_local - 1) >> 1) & 1));
     }
     tc::fence_before_sync();
     __syncthreads();
