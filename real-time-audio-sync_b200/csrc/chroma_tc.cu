@@ -137,6 +137,16 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile(
 #ifndef AFS_TC_WAIT_NS
 #define AFS_TC_WAIT_NS 200
 #endif
+// The only waits that span CTAs are the two ring counters.  They cannot deadlock (see the publisher), but a wait on another
+// CTA is where a bug would turn into a hung GPU, so they are bounded: after kRingWaitNs the kernel traps (the launch fails
+// with an error instead of never returning).
+constexpr unsigned long long kRingWaitNs = 4000000000ull;
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity)
 {
     uint32_t done;
@@ -292,7 +302,11 @@ __device__ __noinline__ void filterbank_role(const SpectrumArgs &args, unsigned 
             if (lane == 0) {
                 const int64_t left = n_groups - tile * kFbGroups;
                 const int want = use * kFbGroups + (int)(left < kFbGroups ? left : kFbGroups);
-                while (afs::ld_acquire(args.prod + slot) < want) __nanosleep(100);
+                const unsigned long long t0 = global_ns();
+                while (afs::ld_acquire(args.prod + slot) < want) {
+                    __nanosleep(100);
+                    if (global_ns() - t0 > kRingWaitNs) __trap();
+                }
                 // the tile was written with ordinary stores by other SMs; the bulk copies below read it through the async proxy
                 asm volatile("fence.proxy.async.global;" ::: "memory");
             }
@@ -716,34 +730,44 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
             slot = (int)(tile % args.ring_tiles);
             use = (int)(tile / args.ring_tiles);
         };
-        auto wait_slot_free = [&](int gi) {
-            int slot, use;
-            slot_of(gi, slot, use);
-            if (lane == 0) {
-                // the slot's previous tile must have been consumed by its filterbank CTA
-                while (afs::ld_acquire(args.cons + slot) < use) __nanosleep(100);
-                mbar_arrive(&s_bar[kBarSlotOk + (gi & 1)]);
+        // Two duties, polled without ever blocking one on the other (a publisher that waits for a slot while it holds back
+        // a stored group deadlocks a small ring: the slot may only free up once that very group has been published):
+        //   q: next group whose ring slot must be confirmed free (at most two groups ahead of the epilogue: two barriers)
+        //   p: next group to publish once the epilogue warps have stored it
+        int pg = 0, qg = 0;
+        unsigned long long t_idle = global_ns();
+        while (pg < n_local) {
+            bool progress = false;
+            if (qg < n_local && qg < pg + 2) {
+                int slot, use;
+                slot_of(qg, slot, use);
+                int ok = 0;
+                if (lane == 0) ok = afs::ld_acquire(args.cons + slot) >= use;       // the slot's previous tile has been consumed
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                if (ok) {
+                    if (lane == 0) mbar_arrive(&s_bar[kBarSlotOk + (qg & 1)]);
+                    qg++;
+                    progress = true;
+                }
             }
-            __syncwarp();
-        };
-        // the slot checks run two groups ahead of the epilogue (two barriers, alternating), so their L2 round trip is never
-        // on the epilogue's path
-        wait_slot_free(0);
-        if (n_local > 1) wait_slot_free(1);
-        for (int gi = 0; gi < n_local; gi++) {
-            int slot, use;
-            slot_of(gi, slot, use);
-            mbar_wait_sleep(&s_bar[kBarStored], (uint32_t)(gi & 1));
-            trace(0, gi);
-            if (lane == 0) {
-                __threadfence();
-                trace(3, gi);
-                atomicAdd(args.prod + slot, 1);
+            if (mbar_try(&s_bar[kBarStored], (uint32_t)(pg & 1))) {
+                int slot, use;
+                slot_of(pg, slot, use);
+                if (lane == 0) {
+                    __threadfence();
+                    atomicAdd(args.prod + slot, 1);
+                }
+                __syncwarp();
+                trace(1, pg);
+                pg++;
+                progress = true;
             }
-            __syncwarp();
-            trace(1, gi);
-            if (gi + 2 < n_local) wait_slot_free(gi + 2);
-            trace(2, gi);
+            if (progress) {
+                t_idle = global_ns();
+            } else {
+                __nanosleep(100);
+                if (global_ns() - t_idle > kRingWaitNs) __trap();
+            }
         }
     } else if (warp > kWarpsC + kWarpsE1 + kWarpsE2) {
         // ================= L: audio -> ring.  A piece (1024 consecutive samples) that lies inside its track and

@@ -192,3 +192,41 @@ def test_create_stft_is_the_reference_spectrum(chroma, audio, orc):
     assert np.abs(c1 - c2).max() < 1e-9
     c3 = chroma.create_chroma(got)                      # the object create_stft returned: fused path from the samples
     assert np.abs(c3 - c2).max() < 1e-4
+
+
+@pytest.mark.parametrize("pcm", [False, True])
+def test_tensor_core_path_many_short_ragged_tracks(chroma, orc, pcm, monkeypatch):
+    """The fused tcgen05 launch on the shapes its fast paths do not cover: hundreds of short tracks of random length, so that
+    almost every 2-frame tile straddles two tracks (the converter's guarded loads), every track has zero-padded first and
+    last frames (the loader's guarded copies), and — with a 4-tile ring and 3 filterbank CTAs on a fresh plan — the
+    power-spectrum ring wraps dozens of times (slot hand-back between the spectrum and the filterbank CTAs)."""
+    import torch
+    monkeypatch.setenv("AFS_CHROMA_TC_RING", "4")
+    monkeypatch.setenv("AFS_CHROMA_TC_FB", "3")
+    plan = chroma.ChromaPlan(chroma.fft_len, chroma.hop_size)
+    rng = np.random.default_rng(21 + pcm)
+    tracks = []
+    for k in range(420):
+        n = int(rng.integers(2048, 14000))
+        t = np.arange(n) / 22050.0
+        x = 0.3 * np.sin(2 * np.pi * float(rng.uniform(80, 4000)) * t) + 0.05 * rng.standard_normal(n)
+        tracks.append(np.round(x * 20000).astype(np.int16) if pcm else x.astype(np.float32))
+    q = 8 if pcm else 4
+    lens = [(len(t) + q - 1) // q * q for t in tracks]
+    offs = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    flat = np.zeros(int(offs[-1]), dtype=np.int16 if pcm else np.float32)
+    for k, t in enumerate(tracks):
+        flat[offs[k] : offs[k] + len(t)] = t
+    d_out, foffs = plan.run(torch.from_numpy(flat).cuda(), offs, out_dtype=torch.float64, compute="tc")
+    host = d_out.cpu().numpy()
+    assert int(foffs[-1]) > 64 * 4 * 4            # the 4-slot ring wrapped several times
+    worst = 0.0
+    for k, t in enumerate(tracks):
+        x = np.zeros(lens[k], dtype=np.float32)
+        x[: len(t)] = (t.astype(np.float32) / np.float32(32768.0)) if pcm else t
+        want = orc.wav_samples_to_chroma(x)
+        got = host[12 * foffs[k] : 12 * foffs[k + 1]].reshape(12, -1)
+        assert got.shape == want.shape, k
+        worst = max(worst, float(np.abs(got - want).max()))
+    assert worst < TOL_F32, worst
+    plan.close() if hasattr(plan, "close") else None
