@@ -560,6 +560,19 @@ def bench_dtw(ctx):
         step_e2e()
     barrier()
     e2e_serial_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    # what limits e2e when all ranks upload at once: this rank's host -> device rate with every rank copying concurrently
+    # (CUDA events around the two uploads alone, three repetitions, slowest rank reported)
+    up0, up1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    up0.record()
+    for _ in range(3):
+        da = h_a.to("cuda", non_blocking=True)
+        db = h_b.to("cuda", non_blocking=True)
+    up1.record()
+    torch.cuda.synchronize()
+    up_bytes = 3 * (h_a.numel() * h_a.element_size() + h_b.numel() * h_b.element_size())
+    h2d_gbs_slowest = up_bytes / max_over_ranks(up0.elapsed_time(up1) * 1e-3) / 1e9
+    del da, db
 
     # The same work as a stream of batches (what a service does), through the public `dtw.DtwPipeline`: two batches are in
     # flight on two plans / two compute streams, so the ramp-down of one launch and its backtrack overlap the ramp-up of
@@ -678,6 +691,7 @@ def bench_dtw(ctx):
                 "mode": "dtw.DtwPipeline(depth=2): a stream of batches, two in flight on two plans / compute streams; a batch's "
                         "upload and read-back overlap the neighbouring batch's kernels (copy stream + events); every step's own "
                         "copies are inside the timed region",
+                "h2d_gbs_per_rank_all_ranks_copying": h2d_gbs_slowest,
                 "serial_value": e2e_serial_val,
                 "serial_note": "one batch at a time: upload, K2, K3, read-back, synchronize"},
         "gpu_launches": int(launches),
