@@ -497,12 +497,13 @@ def bench_dtw(ctx):
     step_mode = "one step at a time on one stream (256 MiB L2 flush between steps)"
     if 2 * P <= DTW_PAIRS_PER_GPU:
         # A rank's share is a fraction of the batch: a launch of few pairs spends ~6 ms of its ~20 filling and draining the
-        # chain of bands, so consecutive steps alternate between two plans on two streams and the next step's bands fill the
-        # SMs the previous one vacates.  Every step is still a full accumulate + backtrack of the rank's pairs; the timed
+        # chain of bands, so consecutive steps rotate over three plans on three streams and the next steps' bands fill the
+        # SMs the previous one vacates (measured at 32 pairs per GPU: 24.5 ms per step alone, 24.3 with two in flight, 22.3
+        # with three, no further gain with four).  Every step is still a full accumulate + backtrack of the rank's pairs; the timed
         # region is K steps between one start event and the later of the two streams' end events.
-        plan_b = dtw.DtwPlan([Ln] * P, [Ln] * P, dtype=args.dtype)
-        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
-        plans = [plan, plan_b]
+        depth = max(2, env_int("AFS_BENCH_DTW_DEPTH", 3))
+        plans = [plan] + [dtw.DtwPlan([Ln] * P, [Ln] * P, dtype=args.dtype) for _ in range(depth - 1)]
+        streams = [torch.cuda.Stream() for _ in range(depth)]
 
         def run_steps(k_steps):
             e0 = torch.cuda.Event(enable_timing=True)
@@ -510,9 +511,9 @@ def bench_dtw(ctx):
             for st in streams:
                 st.wait_event(e0)
             for k in range(k_steps):
-                with torch.cuda.stream(streams[k & 1]):
-                    plans[k & 1].accumulate(d_a, d_b)
-                    plans[k & 1].backtrack()
+                with torch.cuda.stream(streams[k % depth]):
+                    plans[k % depth].accumulate(d_a, d_b)
+                    plans[k % depth].backtrack()
             ends = []
             for st in streams:
                 e1 = torch.cuda.Event(enable_timing=True)
@@ -528,10 +529,11 @@ def bench_dtw(ctx):
         barrier()
         launches = nat.launch_count() - launches0
         step_ms = total_ms / args.steps
-        step_mode = ("steps alternate between two plans on two streams (the next step's bands fill the SMs the previous step "
-                     "vacates); no L2 flush: a step writes %.1f GB of direction map, far more than the 126 MB L2" % (cells_rank / 4 / 1e9))
-        plan_b.close()
-        del plan_b
+        step_mode = ("steps rotate over %d plans on %d streams (the next step's bands fill the SMs the previous step "
+                     "vacates); no L2 flush: a step writes %.1f GB of direction map, far more than the 126 MB L2" % (depth, depth, cells_rank / 4 / 1e9))
+        for pb in plans[1:]:
+            pb.close()
+        del plans
     step_ms_max = max_over_ranks(step_ms)
     value = cells_rank * world / (step_ms_max * 1e-3) / 1e9
 
