@@ -197,8 +197,13 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": "dtw_gcups", "value": v, "unit": "GCUPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "offline full DTW 20k x 20k chroma frames, batch of 256 pairs per GPU (BASELINE cfg[2]); CPU arm = bounded sample of 3000x3000 pairs, same arithmetic"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        # same workload as the GPU arm (its `config`, `metric`, `unit`); a step here is a bounded SAMPLE of it — the
+        # 256 x 20k x 20k batch would take the host cores the better part of an hour per step
+        "config": {"workload": "offline full DTW %dx%d chroma frames, one batch of %d pairs sharded over %d GPU(s): %d pairs per GPU (BASELINE cfg[2]; strong scaling)"
+                               % (args.length, args.length, args.pairs, max(1, args.gpus), max(1, args.pairs // max(1, args.gpus))),
+                   "pairs_total": args.pairs, "frames": args.length, "features": 12,
+                   "cpu_sample": "each step times 3000x3000 pairs of the same generator for a fixed wall time on all host threads (GCUPS does not depend on the pair size on the CPU: no wavefront ramp)"},
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
