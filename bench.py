@@ -308,6 +308,7 @@ def main():
         line["chroma_frames_per_s"] = pick("chroma", "value")
         line["chroma_hbm_frac"] = pick("chroma", "roofline", "frac")
         line["chroma_e2e_frames_per_s"] = pick("chroma", "e2e", "value")
+        line["chroma_e2e_pcm16_frames_per_s"] = pick("chroma", "e2e_pcm16", "value")
         line["otw_p99_ms"] = pick("otw", "value")
         line["otw_p50_ms"] = pick("otw", "ms_per_step")
         line["wtw_value"] = pick("wtw", "value")
