@@ -59,18 +59,25 @@ class StreamFrontDoor(object):
         stops = []
         max_f = int(n_frames.max())
         cols = torch.zeros((max_f, self.n, 12), dtype=torch.float64, device=self.batch.device)
-        active = torch.zeros((max_f, self.n), dtype=torch.uint8, device=self.batch.device)
+        active_h = np.zeros((max_f, self.n), dtype=np.uint8)          # host copy: the loop below never indexes a device tensor
         for s in range(self.n):
             k = int(n_frames[s])
             if k:
                 blk = d_chroma[12 * foffs[s] : 12 * foffs[s + 1]].view(12, k)
                 cols[:k, s, :] = blk.t()
-                active[:k, s] = 1
+                active_h[:k, s] = 1
+        active = torch.from_numpy(active_h).to(self.batch.device)
+        # all launches first (asynchronous; the batch reuses its output block, so each step's outputs are copied aside on
+        # the device), one synchronising read-back at the end
+        outs = []
         for q in range(max_f):
             st, npts, pts = self.batch.step_device(cols[q].contiguous(), active=active[q].contiguous())
-            st_h, np_h, pts_h = st.cpu().numpy()[0], npts.cpu().numpy()[0], pts.cpu().numpy()[0]
-            for s in range(self.n):
-                if active[q, s] and not self.stopped[s]:
+            outs.append((st.clone(), npts.clone(), pts.clone()))
+        host = [(st.cpu().numpy()[0], npts.cpu().numpy()[0], pts.cpu().numpy()[0]) for st, npts, pts in outs]
+        for q in range(max_f):
+            st_h, np_h, pts_h = host[q]
+            for s in np.nonzero(active_h[q])[0]:
+                if not self.stopped[s]:
                     if np_h[s] > 0:
                         self.position[s] = (int(pts_h[s, np_h[s] - 1, 0]), int(pts_h[s, np_h[s] - 1, 1]))
                     if st_h[s] == nat.AFS_STEP_STOP:
