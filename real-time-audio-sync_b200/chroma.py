@@ -3,8 +3,8 @@
 Reference: chroma.py:20-90 — ``wav_to_chroma(path)``, ``wav_to_chroma_col(buf)``,
 ``create_stft`` + ``create_chroma`` and ``wav_to_chroma_diff(path)``; globals ``fft_len``,
 ``hop_size``, ``fs``.  Framing, Hann window, real FFT, |X|^2, the 12 x 2049 filterbank
-and the L2 normalisation run fused in kernel K1 (csrc/chroma.cu) through
-``afs_chroma_batch``; WAV decoding stays on the CPU (it only feeds samples).
+and the L2 normalisation run fused in kernel K1 (csrc/chroma_tc.cu on the tensor cores, csrc/chroma.cu on the
+CUDA cores) through ``afs_chroma_batch``; WAV decoding stays on the CPU (it only feeds samples).
 
 Differences from the reference, all explicit:
 * three arithmetic modes: ``compute="tc"`` (default) runs the DFT as two matrix products on the
