@@ -786,10 +786,29 @@ int afs_dtw_plan_create(afs_dtw_plan **out, int n_pairs, const int64_t *h_len_a,
         if (q.nbands > max_bands) max_bands = q.nbands;
         if (q.nchunks * kChunkCols > pl->max_cols_pad) pl->max_cols_pad = q.nchunks * kChunkCols;
     }
-    // ticket order: band-major, pairs interleaved -> every dependency has a smaller ticket
-    for (int b = 0; b < max_bands; b++)
-        for (int p = 0; p < n_pairs; p++)
-            if (b < pl->pairs[p].nbands) pl->items.push_back(DtwItem{p, b});
+    // Ticket order.  Bands are interleaved band-major inside groups of `group` pairs, group after group; every dependency
+    // (band b-1 of the same pair) has a smaller ticket.  Whole batch as one group (default): each pair has (warp slots /
+    // pairs) bands in flight, and in steady state they are spread evenly over the columns — about a millisecond apart — so
+    // every band re-reads its pair's packed seq_b from DRAM once the batch's seq_b (2.2 MB per 20k-column pair) exceeds L2:
+    // 118 GB of DRAM traffic per launch at 256 pairs against 26.6 GB algorithmic.  Small groups keep a pair's bands close
+    // together (64 steps, ~20 us, at group = 1) and the re-reads become L2 hits — measured at 256 pairs (GCUPS, DRAM GB):
+    // batch 645 / 118, 64 pairs 625 / 75, 32: 618 / 51, 16: 612 / 34, 1 (pair-major): 507 / 27.1 = 1.02 x algorithmic.
+    // The kernel is bound by the FP64 pipe, not by DRAM (0.76 TB/s), and every grouping costs ramp at the group edges, so
+    // the default stays the whole batch; AFS_DTW_ORDER=g<N> | p selects the others.
+    // group: pairs per interleaved group (1 = pair-major, n_pairs = band-major over the whole batch)
+    int group = n_pairs;
+    if (const char *o = getenv("AFS_DTW_ORDER")) {
+        if (o[0] == 'p') group = 1;
+        else if (o[0] == 'g') group = atoi(o + 1) > 0 ? atoi(o + 1) : n_pairs;
+    }
+    for (int p0 = 0; p0 < n_pairs; p0 += group) {
+        const int p1 = p0 + group < n_pairs ? p0 + group : n_pairs;
+        int gb = 0;
+        for (int p = p0; p < p1; p++) gb = pl->pairs[p].nbands > gb ? pl->pairs[p].nbands : gb;
+        for (int b = 0; b < gb; b++)
+            for (int p = p0; p < p1; p++)
+                if (b < pl->pairs[p].nbands) pl->items.push_back(DtwItem{p, b});
+    }
     pl->total_bands = prog;
     pl->total_path = path_pairs;
     pl->dir_bytes = afs::align_up((size_t)dir_units * 16, 256);
