@@ -587,7 +587,8 @@ def bench_dtw(ctx):
     # the next; a batch's inputs are uploaded on a copy stream while the previous batch computes, and its paths are read
     # back while the next one computes.  Every step still moves its own inputs host -> device and its own results
     # device -> host inside the timed region.
-    pipe = dtw.DtwPipeline([Ln] * P, [Ln] * P, dtype=args.dtype, depth=2)
+    pipe_depth = 3 if 2 * P <= DTW_PAIRS_PER_GPU else 2          # small shares: three batches in flight, like the device-timed steps
+    pipe = dtw.DtwPipeline([Ln] * P, [Ln] * P, dtype=args.dtype, depth=pipe_depth)
 
     def run_pipelined(n):
         for _ in range(n):
@@ -696,7 +697,7 @@ def bench_dtw(ctx):
         "fp32_mode": other, "weak": weak,
         "wall_s_timed_region": t_wall,
         "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": 2 * e2e_steps,
-                "mode": "dtw.DtwPipeline(depth=2): a stream of batches, two in flight on two plans / compute streams; a batch's "
+                "mode": "dtw.DtwPipeline(depth=%d): a stream of batches, that many in flight on their own plans / compute streams; a batch's " % pipe_depth +
                         "upload and read-back overlap the neighbouring batch's kernels (copy stream + events); every step's own "
                         "copies are inside the timed region",
                 "h2d_gbs_per_rank_all_ranks_copying": h2d_gbs_slowest,
