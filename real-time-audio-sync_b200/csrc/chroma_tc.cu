@@ -290,8 +290,8 @@ __device__ __noinline__ void filterbank_role(const SpectrumArgs &args, unsigned 
     const int64_t n_tiles = (n_frames + kFbTile - 1) / kFbTile;
     const unsigned char *ring = reinterpret_cast<const unsigned char *>(args.p_hi);
     auto trace = [&](int ev, int idx) {
-        if (TRACE && lane == 0 && 4 * idx + ev < 256)
-            args.trace[((size_t)(args.n_spec + blockIdx.x) * (kThreadsA / 32) + warp) * 256 + 4 * idx + ev] = clock64();
+        if (TRACE && lane == 0 && 4 * idx + ev < kTraceLen)
+            args.trace[((size_t)(args.n_spec + blockIdx.x) * (kThreadsA / 32) + warp) * kTraceLen + 4 * idx + ev] = clock64();
     };
 
     if (warp == 0) {
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) chroma_tc_spectrum_kernel(const 
             const int b = gi & 1, u = gi >> 1;
             const int64_t g = sb + (int64_t)gi * args.n_spec;
             const int64_t ring_tile = g / kFbGroups;
-            const int ring_slot = (int)(ring_tile % args.ring_tiles), ring_use = (int)(ring_tile / args.ring_tiles);
+            const int ring_slot = (int)(ring_tile % args.ring_tiles);
             mbar_wait_sleep(&s_bar[kBarM2Done + b], (uint32_t)(u & 1));
             tc::fence_after_sync();
             trace(0, gi);
