@@ -5,7 +5,7 @@
  * from the product package.  Only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may use it.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py runs this file
+ * Parity status: PINNED.  tests/test_oracle_cpu.py runs this file
  * against the unmodified reference sources (oracle/ref_shim.py) in the build
  * container — bit-equal acc_cost matrices and identical paths — and
  * tests/golden/ holds vectors generated from the reference itself, including

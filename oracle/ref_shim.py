@@ -7,7 +7,7 @@ the build container (``/root/reference`` is absent on the GPU box), so it is
 used for exactly two things:
 
 * ``tests/golden/make_golden.py`` — generate the committed golden vectors;
-* ``tests/test_oracle_vs_reference.py`` — pin the C/numpy restatement in
+* ``tests/test_oracle_cpu.py`` — pin the C/numpy restatement in
   ``oracle/`` against the real reference (skipped when the tree is absent).
 
 Nothing in the product package may import this module.
