@@ -33,6 +33,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
+#include <mutex>
 
 #include "chroma_tc.cuh"
 #include "tc05.cuh"
@@ -915,12 +916,17 @@ struct afs_chroma_tc {
     int *flags = nullptr;             // [2][ring_tiles]: prod | cons
     int ring_tiles = 48;              // 48 x 590 KB = 28 MB: stays in L2
     int n_fb = 16;                    // CTAs that run the filterbank role
+    // the ring and its counters belong to the plan: launches of one plan from different streams or threads are put in
+    // order on the device (each waits for the previous one's completion event) instead of sharing them concurrently
+    std::mutex mu;
+    cudaEvent_t done = nullptr;
 };
 
 void chroma_tc_destroy(afs_chroma_tc *tc)
 {
     if (!tc) return;
     cudaFree(tc->f_img); cudaFree(tc->w_img); cudaFree(tc->g_img); cudaFree(tc->tw); cudaFree(tc->hann); cudaFree(tc->ring); cudaFree(tc->flags);
+    if (tc->done) cudaEventDestroy(tc->done);
     delete tc;
 }
 
@@ -1023,6 +1029,7 @@ int chroma_tc_create(afs_chroma_tc **out, const std::vector<double> &fb, const s
     }
     cudaError_t e2 = cudaMalloc(&tcp->ring, sizeof(uint32_t) * 2 * (size_t)tcp->ring_tiles * kFbTile * kPlaneWords);
     if (e2 == cudaSuccess) e2 = cudaMalloc(&tcp->flags, sizeof(int) * 2 * tcp->ring_tiles);
+    if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&tcp->done, cudaEventDisableTiming);
     if (e2 != cudaSuccess) {
         chroma_tc_destroy(tcp);
         return afs::fail(AFS_ERR_CUDA, "chroma_tc_create: %s", cudaGetErrorString(e2));
@@ -1037,6 +1044,8 @@ int chroma_tc_run(afs_chroma_tc *tcp, const ChromaBatch &bt, cudaStream_t st)
     // persistent and every CTA is resident (grid <= number of SMs, one CTA per SM), which the hand-off through the
     // power-spectrum ring relies on.
     if (bt.total_frames <= 0) return AFS_OK;
+    std::lock_guard<std::mutex> lock(tcp->mu);
+    AFS_CUDA(cudaStreamWaitEvent(st, tcp->done, 0));      // the previous launch of this plan has released the ring
     const int n_sm = afs::sm_count();
     const int64_t groups = (bt.total_frames + 3) / 4, tiles = (bt.total_frames + kFbTile - 1) / kFbTile;
     SpectrumArgs sa;
@@ -1081,6 +1090,7 @@ int chroma_tc_run(afs_chroma_tc *tcp, const ChromaBatch &bt, cudaStream_t st)
     else chroma_tc_spectrum_kernel<false, false><<<blocks, kThreadsA, kSmemA, st>>>(sa);
     afs::count_launch();
     AFS_CUDA(cudaGetLastError());
+    AFS_CUDA(cudaEventRecord(tcp->done, st));
     if (trace_path) {
         std::vector<long long> host(trace_n);
         AFS_CUDA(cudaMemcpyAsync(host.data(), sa.trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost, st));

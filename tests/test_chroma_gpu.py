@@ -230,3 +230,26 @@ def test_tensor_core_path_many_short_ragged_tracks(chroma, orc, pcm, monkeypatch
         worst = max(worst, float(np.abs(got - want).max()))
     assert worst < TOL_F32, worst
     plan.close() if hasattr(plan, "close") else None
+
+
+def test_one_plan_from_two_streams(chroma, orc):
+    """Two launches of the same plan on different streams share the plan's power-spectrum ring: the library orders them on
+    the device instead of letting them run into each other (plan state rewritten under a running kernel)."""
+    import torch
+    rng = np.random.default_rng(5)
+    plan = chroma.default_plan()
+    xs = [(0.2 * rng.standard_normal(22050 * 20)).astype(np.float32) for _ in range(2)]
+    want = [orc.wav_samples_to_chroma(x) for x in xs]
+    d = [torch.from_numpy(x).cuda() for x in xs]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    torch.cuda.synchronize()
+    for rep in range(6):
+        for k in range(2):
+            with torch.cuda.stream(streams[k]):
+                o, foffs = plan.run(d[k], [0, len(xs[k])], out_dtype=torch.float64)
+                outs.append((k, o))
+    torch.cuda.synchronize()
+    for k, o in outs:
+        got = o.cpu().numpy().reshape(12, -1)
+        assert np.abs(got - want[k]).max() < TOL_F32
