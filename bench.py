@@ -587,7 +587,7 @@ def bench_dtw(ctx):
     # the next; a batch's inputs are uploaded on a copy stream while the previous batch computes, and its paths are read
     # back while the next one computes.  Every step still moves its own inputs host -> device and its own results
     # device -> host inside the timed region.
-    pipe_depth = 3 if 2 * P <= DTW_PAIRS_PER_GPU else 2          # small shares: three batches in flight, like the device-timed steps
+    pipe_depth = env_int("AFS_BENCH_PIPE_DEPTH", 3)     # three batches in flight (measured at 256 pairs: 609 GCUPS with two, 621 with three)
     pipe = dtw.DtwPipeline([Ln] * P, [Ln] * P, dtype=args.dtype, depth=pipe_depth)
 
     def run_pipelined(n):
